@@ -1,0 +1,158 @@
+"""Seeded synthetic PacBio-CLR-like data for the fc_consensus hot path.
+
+Uniform-random genome, reads sampled uniformly on both strands, per-base error model
+ins 9 % / del 4.5 % / sub 1.5 % (15 % total), seed blocks built from ground truth (every read
+overlapping the seed by >= ``min_ovl`` bases on the genome, oriented to the seed's strand, whole
+read -- what ``LA4Falcon -fo`` hands to ``fc_consensus``; reference consumer:
+falcon_kit/mains/consensus.py:161-209).
+
+Two output shapes:
+  * a *read pool* (distinct sequences + per-block index lists) for the resident-read-store path;
+  * LA4Falcon block text (``"%08d SEQ"`` lines, ``+ +`` after each block, ``- -`` at the end)
+    for the drop-in CLI path.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Iterator, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+_ASCII = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+
+def random_codes(n: int, rng: np.random.Generator) -> np.ndarray:
+    return rng.integers(0, 4, size=n, dtype=np.uint8)
+
+
+def codes_to_bytes(codes: np.ndarray) -> bytes:
+    return _ASCII[codes].tobytes()
+
+
+def revcomp_codes(codes: np.ndarray) -> np.ndarray:
+    return (3 - codes[::-1]).astype(np.uint8)
+
+
+def add_errors(tmpl: np.ndarray, rng: np.random.Generator, p_ins: float = 0.09,
+               p_del: float = 0.045, p_sub: float = 0.015) -> np.ndarray:
+    """Apply the CLR-like error model to a template (uint8 codes)."""
+    n = tmpl.shape[0]
+    keep = rng.random(n) >= p_del
+    out = tmpl.copy()
+    sub = rng.random(n) < p_sub
+    out[sub] = (out[sub] + rng.integers(1, 4, size=int(sub.sum()), dtype=np.uint8)) & 3
+    # geometric insertion run after each template base, mean p_ins
+    r = p_ins / (1.0 + p_ins)
+    n_ins = rng.geometric(1.0 - r, size=n) - 1
+    reps = keep.astype(np.int64) + n_ins
+    total = int(reps.sum())
+    res = np.repeat(out, reps)
+    # positions that are inserted bases: everything except the first copy of a kept base
+    starts = np.cumsum(reps) - reps
+    is_tmpl = np.zeros(total, dtype=bool)
+    is_tmpl[starts[keep & (reps > 0)]] = True
+    ins_mask = ~is_tmpl
+    res[ins_mask] = rng.integers(0, 4, size=int(ins_mask.sum()), dtype=np.uint8)
+    return res
+
+
+@dataclass
+class SynthSet:
+    """A read pool plus seed blocks that index into it."""
+    pool: List[bytes]                      # distinct sequences (ASCII, upper-case ACGT)
+    blocks: List[np.ndarray]               # per block: int32 pool indices, [0] = seed
+    seed_ids: List[str]                    # printable seed id per block
+    streams: List[np.ndarray] = field(default_factory=list)  # per block: LA4Falcon stream order
+    read_len: int = 0
+    genome_size: int = 0
+    meta: dict = field(default_factory=dict)
+
+    @property
+    def n_pairs(self) -> int:
+        return int(sum(len(b) - 1 for b in self.blocks))
+
+    def block_seqs(self, bi: int) -> List[bytes]:
+        return [self.pool[i] for i in self.blocks[bi]]
+
+    def la4falcon_text(self, block_ids: Optional[Sequence[int]] = None) -> bytes:
+        """LA4Falcon-style stream for the CLI path.  The first line of each block is the seed
+        itself (the parser appends it twice by design, consensus.py:183-190), then the reads."""
+        out = []
+        ids = range(len(self.blocks)) if block_ids is None else block_ids
+        for bi in ids:
+            idx = self.streams[bi]
+            out.append(b"%s %s\n" % (self.seed_ids[bi].encode(), self.pool[idx[0]]))
+            for pi in idx[1:]:
+                out.append(b"%08d %s\n" % (90000000 + int(pi), self.pool[pi]))
+            out.append(b"+ +\n")
+        out.append(b"- -\n")
+        return b"".join(out)
+
+
+def make_set(genome_size: int, read_len: int, coverage: float, seed: int = 20260924,
+             n_blocks: Optional[int] = None, min_ovl: int = 1000, max_n_read: int = 200,
+             len_sigma: float = 0.0, p_ins: float = 0.09, p_del: float = 0.045,
+             p_sub: float = 0.015, block_stride: int = 1) -> SynthSet:
+    """Build a synthetic set.  Each read contributes two pool entries (forward-strand noisy copy
+    and its reverse complement); a block uses the orientation of its seed for every member.
+
+    Block layout mirrors what get_seq_data + get_longest_reads produce
+    (consensus.py:26-45,161-209): ``[seed, seed, reads sorted by -len (stable)]`` capped at
+    ``max_n_read`` entries.
+    """
+    rng = np.random.default_rng(seed)
+    genome = random_codes(genome_size, rng)
+    n_reads = max(2, int(round(genome_size * coverage / read_len)))
+    if len_sigma > 0:
+        mu = np.log(read_len) - 0.5 * len_sigma ** 2
+        lens = np.clip(rng.lognormal(mu, len_sigma, n_reads).astype(np.int64), 1000,
+                       min(genome_size, 99000))
+    else:
+        lens = np.full(n_reads, min(read_len, genome_size), dtype=np.int64)
+    starts = (rng.random(n_reads) * (genome_size - lens + 1)).astype(np.int64)
+    order = np.argsort(starts, kind="stable")
+    starts, lens = starts[order], lens[order]
+    ends = starts + lens
+    strands = rng.integers(0, 2, n_reads)
+
+    pool: List[bytes] = []
+    noisy_len = np.zeros(n_reads, dtype=np.int64)
+    for r in range(n_reads):
+        fwd = add_errors(genome[starts[r]:ends[r]], rng, p_ins, p_del, p_sub)
+        if fwd.shape[0] > 99998:
+            fwd = fwd[:99998]
+        noisy_len[r] = fwd.shape[0]
+        pool.append(codes_to_bytes(fwd))
+        pool.append(codes_to_bytes(revcomp_codes(fwd)))
+
+    blocks: List[np.ndarray] = []
+    seed_ids: List[str] = []
+    streams: List[np.ndarray] = []
+    max_len = int(lens.max())
+    seeds = range(0, n_reads, block_stride)
+    for s in seeds:
+        if n_blocks is not None and len(blocks) >= n_blocks:
+            break
+        lo = int(np.searchsorted(starts, starts[s] - max_len, side="left"))
+        hi = int(np.searchsorted(starts, ends[s], side="left"))
+        cand = np.arange(lo, hi)
+        ovl = np.minimum(ends[cand], ends[s]) - np.maximum(starts[cand], starts[s])
+        members = cand[(ovl >= min_ovl) & (cand != s)]
+        # stable sort by -len, as get_longest_reads does on the noisy sequences
+        members = members[np.argsort(-noisy_len[members], kind="stable")]
+        o = int(strands[s])  # 0: forward copies, 1: reverse-complement copies
+        idx = [2 * s + o, 2 * s + o] + [2 * int(m) + o for m in members]
+        stream = np.asarray([idx[0]] + idx[2:], dtype=np.int32)
+        # the duplicated seed copy takes part in the stable sort too (it is seqs[1])
+        rest = idx[1:]
+        rest_len = np.array([len(pool[i]) for i in rest])
+        rest = [rest[i] for i in np.argsort(-rest_len, kind="stable")]
+        idx = [idx[0]] + rest
+        idx = idx[:max_n_read]
+        blocks.append(np.asarray(idx, dtype=np.int32))
+        seed_ids.append("%08d" % s)
+        streams.append(stream)
+    return SynthSet(pool=pool, blocks=blocks, seed_ids=seed_ids, streams=streams, read_len=read_len,
+                    genome_size=genome_size,
+                    meta=dict(seed=seed, coverage=coverage, p_ins=p_ins, p_del=p_del, p_sub=p_sub,
+                              min_ovl=min_ovl, max_n_read=max_n_read, n_reads=n_reads))
