@@ -1,0 +1,250 @@
+"""ctypes binding of libfalcon_b200.so -- the counterpart of falcon_kit/falcon_kit.py.
+
+The reference binds its C library with ``CDLL(ext_falcon.__file__)`` and attaches argtypes at
+import (falcon_kit/falcon_kit.py:44-122); this module does the same for the B200 library and adds
+the batched ``fcx_*`` entry points (include/falcon_b200.h).  There is no fallback: if the shared
+library is missing or no CUDA device is usable, importing / creating an engine raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfalcon_b200.so")
+
+seq_coor_t = C.c_int
+base_t = C.c_uint8
+
+
+# ---- struct mirrors, same layouts as falcon_kit/falcon_kit.py:19-41,86-106 -------------------
+class KmerLookup(C.Structure):
+    _fields_ = [("start", seq_coor_t), ("last", seq_coor_t), ("count", seq_coor_t)]
+
+
+class KmerMatch(C.Structure):
+    _fields_ = [("count", seq_coor_t), ("query_pos", C.POINTER(seq_coor_t)),
+                ("target_pos", C.POINTER(seq_coor_t))]
+
+
+class AlnRange(C.Structure):
+    _fields_ = [("s1", seq_coor_t), ("e1", seq_coor_t), ("s2", seq_coor_t), ("e2", seq_coor_t),
+                ("score", C.c_long)]
+
+
+class ConsensusData(C.Structure):
+    _fields_ = [("sequence", C.c_char_p), ("eff_cov", C.POINTER(C.c_uint))]
+
+
+class Alignment(C.Structure):
+    _fields_ = [("aln_str_size", seq_coor_t), ("dist", seq_coor_t), ("aln_q_s", seq_coor_t),
+                ("aln_q_e", seq_coor_t), ("aln_t_s", seq_coor_t), ("aln_t_e", seq_coor_t),
+                ("q_aln_str", C.c_char_p), ("t_aln_str", C.c_char_p)]
+
+
+class PairInfo(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("n_match", "s1", "e1", "s2", "e2", "passed_filter",
+                                           "aligned", "dist", "aln_size", "q_e", "t_e", "accepted",
+                                           "n_tags", "trace_cells")]
+
+
+T_NAMES = ("index", "range", "dp", "traceback", "consensus", "total")
+C_NAMES = ("pairs", "dp_pairs", "accepted", "trace_cells", "dp_steps", "aln_cols", "span_bases",
+           "kernel_launches", "waves")
+
+
+def load_library(path: str = LIB_PATH) -> C.CDLL:
+    if not os.path.exists(path):
+        raise ImportError(
+            "falcon_b200: %s not found -- build it with `python -c 'import __graft_entry__ as g; "
+            "g.build()'` (nvcc, sm_100a).  There is no CPU fallback." % path)
+    lib = C.CDLL(path)
+    # legacy symbols (falcon_kit/falcon_kit.py:54-122, falcon_kit/mains/consensus.py:20-23)
+    lib.allocate_kmer_lookup.argtypes = [seq_coor_t]
+    lib.allocate_kmer_lookup.restype = C.POINTER(KmerLookup)
+    lib.init_kmer_lookup.argtypes = [C.POINTER(KmerLookup), seq_coor_t]
+    lib.free_kmer_lookup.argtypes = [C.POINTER(KmerLookup)]
+    lib.allocate_seq.argtypes = [seq_coor_t]
+    lib.allocate_seq.restype = C.POINTER(base_t)
+    lib.init_seq_array.argtypes = [C.POINTER(base_t), seq_coor_t]
+    lib.free_seq_array.argtypes = [C.POINTER(base_t)]
+    lib.allocate_seq_addr.argtypes = [seq_coor_t]
+    lib.allocate_seq_addr.restype = C.POINTER(seq_coor_t)
+    lib.free_seq_addr_array.argtypes = [C.POINTER(seq_coor_t)]
+    lib.add_sequence.argtypes = [seq_coor_t, C.c_uint, C.POINTER(C.c_char), seq_coor_t,
+                                 C.POINTER(seq_coor_t), C.POINTER(C.c_uint8), C.POINTER(KmerLookup)]
+    lib.mask_k_mer.argtypes = [C.c_long, C.POINTER(KmerLookup), C.c_long]
+    lib.find_kmer_pos_for_seq.argtypes = [C.POINTER(C.c_char), seq_coor_t, C.c_uint,
+                                          C.POINTER(seq_coor_t), C.POINTER(KmerLookup)]
+    lib.find_kmer_pos_for_seq.restype = C.POINTER(KmerMatch)
+    lib.free_kmer_match.argtypes = [C.POINTER(KmerMatch)]
+    lib.find_best_aln_range.argtypes = [C.POINTER(KmerMatch), seq_coor_t, seq_coor_t, seq_coor_t]
+    lib.find_best_aln_range.restype = C.POINTER(AlnRange)
+    lib.find_best_aln_range2.argtypes = [C.POINTER(KmerMatch), seq_coor_t, seq_coor_t, seq_coor_t]
+    lib.find_best_aln_range2.restype = C.POINTER(AlnRange)
+    lib.free_aln_range.argtypes = [C.POINTER(AlnRange)]
+    lib.align.argtypes = [C.POINTER(C.c_char), C.c_long, C.POINTER(C.c_char), C.c_long, C.c_long,
+                          C.c_int]
+    lib.align.restype = C.POINTER(Alignment)
+    lib.free_alignment.argtypes = [C.POINTER(Alignment)]
+    lib.generate_consensus.argtypes = [C.POINTER(C.c_char_p), C.c_uint, C.c_uint, C.c_uint,
+                                       C.c_double]
+    lib.generate_consensus.restype = C.POINTER(ConsensusData)
+    lib.free_consensus_data.argtypes = [C.POINTER(ConsensusData)]
+    # batched path
+    lib.fcx_version.restype = C.c_char_p
+    lib.fcx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    lib.fcx_destroy.argtypes = [C.c_void_p]
+    lib.fcx_last_error.argtypes = [C.c_void_p]
+    lib.fcx_last_error.restype = C.c_char_p
+    lib.fcx_host_alloc.argtypes = [C.c_size_t]
+    lib.fcx_host_alloc.restype = C.c_void_p
+    lib.fcx_host_free.argtypes = [C.c_void_p]
+    lib.fcx_pool_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+    lib.fcx_consensus_blocks.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint,
+                                         C.c_uint, C.c_double, C.POINTER(C.c_void_p),
+                                         C.POINTER(C.c_void_p)]
+    lib.fcx_last_pair_info.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    lib.fcx_last_stats.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+    return lib
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        _lib = load_library()
+    return _lib
+
+
+# the three names the reference exports for one and the same CDLL (falcon_kit.py:52,109,117)
+def kup() -> C.CDLL:
+    return lib()
+
+
+DWA = kup
+falcon = kup
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class PinnedBuffer:
+    """Page-locked host staging buffer (numpy view) for read bytes."""
+
+    def __init__(self, nbytes: int):
+        self._lib = lib()
+        self.ptr = self._lib.fcx_host_alloc(max(1, nbytes))
+        if not self.ptr:
+            raise EngineError("fcx_host_alloc(%d) failed" % nbytes)
+        self.nbytes = nbytes
+        self.array = np.ctypeslib.as_array((C.c_uint8 * max(1, nbytes)).from_address(self.ptr))
+
+    def close(self):
+        if self.ptr:
+            self._lib.fcx_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Engine:
+    """One GPU engine (one per process per GPU)."""
+
+    def __init__(self, device: int = 0):
+        self._lib = lib()
+        h = C.c_void_p()
+        if self._lib.fcx_create(device, C.byref(h)) != 0:
+            raise EngineError("fcx_create(%d): %s" % (device, self._lib.fcx_last_error(None).decode()))
+        self._h = h
+        self.n_reads = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.fcx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise EngineError("%s: %s" % (what, self._lib.fcx_last_error(self._h).decode()))
+
+    # -- pool ---------------------------------------------------------------------------
+    def upload_pool_raw(self, bases_ptr: int, offsets: np.ndarray):
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = offsets.shape[0] - 1
+        self._check(self._lib.fcx_pool_upload(self._h, bases_ptr, offsets.ctypes.data, n),
+                    "fcx_pool_upload")
+        self.n_reads = n
+
+    def upload_pool(self, reads: Sequence[bytes]):
+        offsets = np.zeros(len(reads) + 1, dtype=np.uint64)
+        np.cumsum([len(r) for r in reads], out=offsets[1:])
+        cat = b"".join(reads)
+        buf = C.create_string_buffer(cat, len(cat) + 1)
+        self.upload_pool_raw(C.addressof(buf), offsets)
+
+    # -- consensus ----------------------------------------------------------------------
+    def consensus_blocks_raw(self, block_off: np.ndarray, read_ids: np.ndarray, min_cov: int,
+                             min_idt: float, K: int = 8) -> Tuple[np.ndarray, np.ndarray]:
+        block_off = np.ascontiguousarray(block_off, dtype=np.uint32)
+        read_ids = np.ascontiguousarray(read_ids, dtype=np.uint32)
+        nb = block_off.shape[0] - 1
+        ob, oo = C.c_void_p(), C.c_void_p()
+        self._check(self._lib.fcx_consensus_blocks(self._h, nb, block_off.ctypes.data,
+                                                   read_ids.ctypes.data, min_cov, K, min_idt,
+                                                   C.byref(ob), C.byref(oo)),
+                    "fcx_consensus_blocks")
+        off = np.ctypeslib.as_array((C.c_uint64 * (nb + 1)).from_address(oo.value)).copy()
+        total = int(off[-1])
+        if total:
+            data = np.ctypeslib.as_array((C.c_uint8 * total).from_address(ob.value)).copy()
+        else:
+            data = np.zeros(0, dtype=np.uint8)
+        return data, off
+
+    def consensus_blocks(self, blocks: Sequence[Sequence[int]], min_cov: int, min_idt: float,
+                         K: int = 8) -> List[bytes]:
+        block_off = np.zeros(len(blocks) + 1, dtype=np.uint32)
+        np.cumsum([len(b) for b in blocks], out=block_off[1:])
+        ids = np.concatenate([np.asarray(b, dtype=np.uint32) for b in blocks]) if blocks else \
+            np.zeros(0, dtype=np.uint32)
+        data, off = self.consensus_blocks_raw(block_off, ids, min_cov, min_idt, K)
+        raw = data.tobytes()
+        return [raw[int(off[i]):int(off[i + 1])] for i in range(len(blocks))]
+
+    def generate_consensus(self, seqs: Sequence[bytes], min_cov: int, min_idt: float, K: int = 8) -> bytes:
+        """One seed block given as sequences (seqs[0] = seed), like the reference call."""
+        self.upload_pool(seqs)
+        return self.consensus_blocks([list(range(len(seqs)))], min_cov, min_idt, K)[0]
+
+    # -- diagnostics --------------------------------------------------------------------
+    def pair_info(self) -> List[PairInfo]:
+        n = C.c_uint64()
+        self._lib.fcx_last_pair_info(self._h, None, 0, C.byref(n))
+        arr = (PairInfo * max(1, n.value))()
+        self._lib.fcx_last_pair_info(self._h, arr, n.value, C.byref(n))
+        return list(arr)[: n.value]
+
+    def stats(self) -> dict:
+        t = (C.c_double * len(T_NAMES))()
+        c = (C.c_uint64 * len(C_NAMES))()
+        self._lib.fcx_last_stats(self._h, t, c)
+        d = {"ms_" + k: t[i] for i, k in enumerate(T_NAMES)}
+        d.update({k: int(c[i]) for i, k in enumerate(C_NAMES)})
+        return d

@@ -1,0 +1,168 @@
+/*
+ * falcon_b200.h -- C ABI of libfalcon_b200.so, the B200-native fc_consensus engine.
+ *
+ * Drop-in boundary.  Two groups of entry points:
+ *
+ *  (1) LEGACY symbols -- exactly what falcon_kit/falcon_kit.py binds from the reference's
+ *      falcon.so (reference: falcon_kit/falcon_kit.py:54-122, src/c/common.h:59-177).  Same names,
+ *      same struct layouts, same ownership rules (callee allocates with malloc/calloc, caller
+ *      releases with the matching free_* function).  generate_consensus() and align() run on the
+ *      GPU (batch of one); the k-mer helper symbols operate on caller-visible host structures
+ *      whose layout is part of the ABI and are host code.
+ *
+ *  (2) BATCHED symbols (fcx_*) -- the throughput path: a resident 2-bit read pool plus seed
+ *      blocks that index into it; one call runs k-mer range finding, the banded O(ND) DP, the
+ *      traceback and the alignment-graph consensus for every block on the device.
+ *
+ * No torch types, no C++ types: plain pointers and sizes.  All functions are synchronous with
+ * respect to the host unless stated otherwise.  Errors: fcx_* return 0 on success, non-zero on
+ * failure with a message in fcx_last_error(); the legacy symbols have no error channel in the
+ * reference (it abort()s, DW_banded.c:100-113, falcon.c:343,476) and abort() here as well.
+ */
+#ifndef FALCON_B200_H
+#define FALCON_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------------------------------------------------------- legacy types (common.h) */
+typedef int seq_coor_t;                                   /* common.h:57 */
+
+typedef struct {                                          /* common.h:59-69 */
+    seq_coor_t aln_str_size;
+    seq_coor_t dist;
+    seq_coor_t aln_q_s;
+    seq_coor_t aln_q_e;
+    seq_coor_t aln_t_s;
+    seq_coor_t aln_t_e;
+    char *q_aln_str;
+    char *t_aln_str;
+} alignment;
+
+typedef struct {                                          /* common.h:95-99 */
+    seq_coor_t start;
+    seq_coor_t last;
+    seq_coor_t count;
+} kmer_lookup;
+
+typedef unsigned char base;                               /* common.h:101-104 */
+typedef base *seq_array;
+typedef seq_coor_t seq_addr;
+typedef seq_addr *seq_addr_array;
+
+typedef struct {                                          /* common.h:107-111 */
+    seq_coor_t count;
+    seq_coor_t *query_pos;
+    seq_coor_t *target_pos;
+} kmer_match;
+
+typedef struct {                                          /* common.h:114-120 */
+    seq_coor_t s1, e1, s2, e2;
+    long int score;
+} aln_range;
+
+typedef struct {                                          /* common.h:123-126 */
+    char *sequence;
+    int *eqv;
+} consensus_data;
+
+/* ---------------------------------------------------------------- legacy entry points */
+/* replaces src/c/falcon.c:562-666; bound at falcon_kit/mains/consensus.py:20-23 */
+consensus_data *generate_consensus(char **input_seq, unsigned int n_seq, unsigned min_cov,
+                                   unsigned K, double min_idt);
+/* replaces src/c/falcon.c:776-780 */
+void free_consensus_data(consensus_data *);
+
+/* replaces src/c/DW_banded.c:115-330; bound at falcon_kit/falcon_kit.py:111-114 */
+alignment *align(char *query_seq, seq_coor_t q_len, char *target_seq, seq_coor_t t_len,
+                 seq_coor_t band_tolerance, int get_aln_str);
+void free_alignment(alignment *);                         /* DW_banded.c:333-337 */
+
+/* k-mer helpers, replace src/c/kmer_lookup.c:71-119,140-204,207-292,294-427,429-589;
+ * bound at falcon_kit/falcon_kit.py:54-83 */
+kmer_lookup *allocate_kmer_lookup(seq_coor_t size);
+void init_kmer_lookup(kmer_lookup *, seq_coor_t size);
+void free_kmer_lookup(kmer_lookup *);
+seq_array allocate_seq(seq_coor_t size);
+void init_seq_array(seq_array, seq_coor_t size);
+void free_seq_array(seq_array);
+seq_addr_array allocate_seq_addr(seq_coor_t size);
+void free_seq_addr_array(seq_addr_array);
+void add_sequence(seq_coor_t start, unsigned int K, char *seq, seq_coor_t seq_len,
+                  seq_addr_array sda, seq_array sa, kmer_lookup *lk);
+void mask_k_mer(seq_coor_t size, kmer_lookup *kl, seq_coor_t threshold);
+kmer_match *find_kmer_pos_for_seq(char *seq, seq_coor_t seq_len, unsigned int K,
+                                  seq_addr_array sda, kmer_lookup *lk);
+void free_kmer_match(kmer_match *);
+aln_range *find_best_aln_range(kmer_match *, seq_coor_t K, seq_coor_t bin_size,
+                               seq_coor_t count_th);
+aln_range *find_best_aln_range2(kmer_match *, seq_coor_t K, seq_coor_t bin_width,
+                                seq_coor_t count_th);
+void free_aln_range(aln_range *);
+
+/* ---------------------------------------------------------------- batched GPU path */
+typedef struct fcx_ctx fcx_ctx;
+
+/* Create an engine bound to CUDA device `device` (one engine per process per GPU). */
+int fcx_create(int device, fcx_ctx **out);
+void fcx_destroy(fcx_ctx *);
+/* Last error text for this engine (ctx may be NULL for creation errors). */
+const char *fcx_last_error(const fcx_ctx *);
+
+/* Pinned host staging memory for the caller's read bytes (optional; plain memory also works). */
+void *fcx_host_alloc(size_t bytes);
+void fcx_host_free(void *);
+
+/* Upload a read pool: n_reads upper-case ACGT sequences stored back to back in `bases`
+ * (no terminators needed), read r = bases[offsets[r] .. offsets[r+1]).  The pool is 2-bit packed
+ * on the device and stays resident until the next fcx_pool_upload / fcx_destroy.  Any byte
+ * outside "ACGT" is an error (the reference's behaviour is undefined for it: falcon.c:370-379
+ * indexes base[-1]). */
+int fcx_pool_upload(fcx_ctx *, const char *bases, const uint64_t *offsets, uint32_t n_reads);
+
+/* Consensus for n_blocks seed blocks.  Block b consists of pool reads
+ * read_ids[block_off[b] .. block_off[b+1]); the first is the seed (target), the rest are aligned
+ * to it in order (exactly the char** order of the reference's generate_consensus).
+ * K must be 8 (falcon_kit/mains/consensus.py:270).
+ * Results: *out_bases is one buffer holding the consensus strings back to back,
+ * block b = [(*out_off)[b], (*out_off)[b+1]); both buffers are owned by the engine and stay
+ * valid until the next fcx_consensus_blocks / fcx_destroy on this engine. */
+int fcx_consensus_blocks(fcx_ctx *, uint32_t n_blocks, const uint32_t *block_off,
+                         const uint32_t *read_ids, unsigned min_cov, unsigned K, double min_idt,
+                         const char **out_bases, const uint64_t **out_off);
+
+/* Per-pair diagnostics of the last fcx_consensus_blocks call (pair p = the p-th non-seed read in
+ * block order).  Used by the parity tests to compare stage by stage with the oracle. */
+typedef struct {
+    int32_t n_match;               /* k-mer hits */
+    int32_t s1, e1, s2, e2;        /* chosen ranges */
+    int32_t passed_filter;         /* falcon.c:613-619 */
+    int32_t aligned;               /* DP reached an end */
+    int32_t dist;                  /* D */
+    int32_t aln_size;              /* A */
+    int32_t q_e, t_e;
+    int32_t accepted;              /* falcon.c:629 */
+    int32_t n_tags;                /* alignment columns voted */
+    int32_t trace_cells;           /* E */
+} fcx_pair_info;
+int fcx_last_pair_info(fcx_ctx *, fcx_pair_info *out, uint64_t max_pairs, uint64_t *n_pairs);
+
+/* Device-side timings (CUDA events on the engine's stream) of the last fcx_consensus_blocks call,
+ * in milliseconds, and work counters.  Index with the FCX_T_* / FCX_C_* constants. */
+enum { FCX_T_INDEX = 0, FCX_T_RANGE, FCX_T_DP, FCX_T_TRACEBACK, FCX_T_CONSENSUS, FCX_T_TOTAL,
+       FCX_T_COUNT };
+enum { FCX_C_PAIRS = 0, FCX_C_DP_PAIRS, FCX_C_ACCEPTED, FCX_C_TRACE_CELLS, FCX_C_DP_STEPS,
+       FCX_C_ALN_COLS, FCX_C_SPAN_BASES, FCX_C_KERNEL_LAUNCHES, FCX_C_WAVES, FCX_C_COUNT };
+int fcx_last_stats(fcx_ctx *, double *times_ms /*FCX_T_COUNT*/, uint64_t *counters /*FCX_C_COUNT*/);
+
+/* Library identification: returns e.g. "falcon_b200 0.1 sm_100a". */
+const char *fcx_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FALCON_B200_H */
