@@ -69,6 +69,7 @@ struct fcx_ctx {
     double times[FCX_T_COUNT] = {0};
     uint64_t counters[FCX_C_COUNT] = {0};
     cudaEvent_t ev[8] = {nullptr};
+    cudaEvent_t tev[2] = {nullptr, nullptr};
     size_t arena_budget = (size_t)40 << 30;
     uint32_t max_wave_blocks = 4096;
     uint32_t max_wave_pairs = 1u << 19;
@@ -111,6 +112,7 @@ extern "C" int fcx_create(int device, fcx_ctx** out) {
         delete ctx; return 1;
     }
     for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+    for (auto& ev : ctx->tev) cudaEventCreate(&ev);
     if (const char* s = getenv("FCX_ARENA_GB")) ctx->arena_budget = (size_t)atof(s) * ((size_t)1 << 30);
     if (const char* s = getenv("FCX_WAVE_BLOCKS")) ctx->max_wave_blocks = (uint32_t)atoi(s);
     if (const char* s = getenv("FCX_WAVE_PAIRS")) ctx->max_wave_pairs = (uint32_t)atoi(s);
@@ -133,6 +135,7 @@ extern "C" void fcx_destroy(fcx_ctx* ctx) {
     HostBuf* hb[] = {&ctx->h_ranges, &ctx->h_aln, &ctx->h_cns, &ctx->h_cnsout, &ctx->h_stage, &ctx->h_eqv};
     for (auto* b : hb) b->release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : ctx->tev) if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -424,6 +427,21 @@ extern "C" int fcx_last_pair_info(fcx_ctx* ctx, fcx_pair_info* out, uint64_t max
 extern "C" int fcx_last_stats(fcx_ctx* ctx, double* times_ms, uint64_t* counters) {
     if (times_ms) memcpy(times_ms, ctx->times, sizeof ctx->times);
     if (counters) memcpy(counters, ctx->counters, sizeof ctx->counters);
+    return 0;
+}
+
+// CUDA-event stopwatch on the engine's stream (bench.py brackets its timed region with it)
+extern "C" int fcx_timer_start(fcx_ctx* ctx) {
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventRecord(ctx->tev[0], ctx->stream));
+    return 0;
+}
+extern "C" int fcx_timer_stop(fcx_ctx* ctx, double* ms) {
+    CK(cudaEventRecord(ctx->tev[1], ctx->stream));
+    CK(cudaEventSynchronize(ctx->tev[1]));
+    float f = 0;
+    CK(cudaEventElapsedTime(&f, ctx->tev[0], ctx->tev[1]));
+    *ms = f;
     return 0;
 }
 

@@ -511,7 +511,7 @@ __global__ void k_traceback(const BlockDesc* __restrict__ blocks, const PairDesc
 // Then the backtrack of falcon.c:479-542 over the stored column records.
 struct CnsRec { int32_t pred; int32_t info; int32_t score2; };   // info = (t_pos << 3) | base
 constexpr int CNS_WARPS = 4;
-constexpr int LINK_CAP = 192;         // distinct (delta, base, link) entries per position
+constexpr int LINK_CAP = 512;         // distinct (delta, base, link) entries per position
 constexpr int LVL = 255 * 5;
 
 struct CnsOut { int32_t len; int32_t err; };

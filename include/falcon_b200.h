@@ -159,6 +159,11 @@ enum { FCX_C_PAIRS = 0, FCX_C_DP_PAIRS, FCX_C_ACCEPTED, FCX_C_TRACE_CELLS, FCX_C
        FCX_C_ALN_COLS, FCX_C_SPAN_BASES, FCX_C_KERNEL_LAUNCHES, FCX_C_WAVES, FCX_C_COUNT };
 int fcx_last_stats(fcx_ctx *, double *times_ms /*FCX_T_COUNT*/, uint64_t *counters /*FCX_C_COUNT*/);
 
+/* CUDA-event stopwatch on the engine's stream: start records an event, stop records a second one,
+ * waits for it and returns the elapsed device time in milliseconds. */
+int fcx_timer_start(fcx_ctx *);
+int fcx_timer_stop(fcx_ctx *, double *ms);
+
 /* Library identification: returns e.g. "falcon_b200 0.1 sm_100a". */
 const char *fcx_version(void);
 

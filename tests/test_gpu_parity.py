@@ -1,0 +1,148 @@
+"""GPU: parity of the CUDA path (through the C ABI) with the CPU oracle and with the golden output
+of the unmodified reference CLI.  Bit-exact: this is integer / byte work."""
+import ctypes as C
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from falcon_b200 import synth
+from helpers import GOLDEN, golden_cases, run_cli
+
+pytestmark = pytest.mark.gpu
+
+FIELDS = ("n_match", "s1", "e1", "s2", "e2", "passed_filter", "aligned", "dist", "aln_size", "q_e", "t_e",
+          "accepted", "n_tags", "trace_cells")
+CASES = golden_cases()
+
+
+def _check_set(engine, oracle, S, min_cov, min_idt=0.70):
+    engine.upload_pool(S.pool)
+    got = engine.consensus_blocks([b.tolist() for b in S.blocks], min_cov, min_idt)
+    info = engine.pair_info()
+    p = 0
+    for bi in range(len(S.blocks)):
+        seqs = S.block_seqs(bi)
+        want, oinfo = oracle.generate_consensus(seqs, min_cov, min_idt, want_info=True)
+        for j in range(1, len(seqs)):
+            g, o = info[p], oinfo[j]
+            for f in FIELDS:
+                if f in ("dist", "aln_size", "q_e", "t_e") and not o.aligned:
+                    continue
+                assert getattr(g, f) == getattr(o, f), "block %d pair %d field %s" % (bi, j, f)
+            p += 1
+        assert got[bi] == want, "block %d consensus differs" % bi
+    assert p == len(info)
+
+
+@pytest.mark.parametrize("params", [
+    dict(genome_size=60000, read_len=5000, coverage=30, seed=1, n_blocks=6),
+    dict(genome_size=40000, read_len=3000, coverage=20, seed=2, n_blocks=4, len_sigma=0.4),
+    dict(genome_size=120000, read_len=15000, coverage=25, seed=3, n_blocks=3),
+    dict(genome_size=50000, read_len=4000, coverage=60, seed=4, n_blocks=3, max_n_read=40),
+    dict(genome_size=50000, read_len=4000, coverage=15, seed=5, n_blocks=4, p_ins=0.05, p_del=0.05, p_sub=0.05),
+])
+def test_stage_parity_with_oracle(engine, oracle, params):
+    _check_set(engine, oracle, synth.make_set(**params), min_cov=4)
+
+
+def test_min_cov_and_idt_variants(engine, oracle):
+    S = synth.make_set(40000, 4000, 25, seed=6, n_blocks=3)
+    for min_cov, min_idt in ((0, 0.70), (1, 0.80), (8, 0.75), (200, 0.70)):
+        _check_set(engine, oracle, S, min_cov, min_idt)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_cli_matches_reference_golden(name, engine):
+    case = CASES[name]
+    stdin = open(os.path.join(GOLDEN, case["input"]), "rb").read()
+    want = open(os.path.join(GOLDEN, name + ".out"), "rb").read()
+    got = run_cli(case["args"], stdin, engine)
+    assert hashlib.md5(got).hexdigest() == case["out_md5"]
+    assert got == want
+
+
+def test_edge_blocks(engine, oracle):
+    rng = np.random.default_rng(1)
+    seed = synth.codes_to_bytes(synth.random_codes(3000, rng))
+    other = synth.codes_to_bytes(synth.random_codes(3000, rng))
+    short = seed[100:106]
+    for seqs in ([seed, seed], [seed, other], [seed], [seed, seed, other, seed[500:2500]], [seed, short, seed],
+                 [seed[:90], seed[:90]], [seed, seed[:600], seed[2400:], seed]):
+        assert engine.generate_consensus(seqs, 0, 0.70) == oracle.generate_consensus(seqs, 0, 0.70)
+
+
+def test_rejects_non_acgt(engine):
+    from falcon_b200.binding import EngineError
+    with pytest.raises(EngineError):
+        engine.upload_pool([b"ACGTNACGT", b"ACGT"])
+    with pytest.raises(EngineError):
+        engine.upload_pool([b"acgt"])
+
+
+def test_legacy_generate_consensus_symbol(oracle):
+    """The reference's own call: falcon.generate_consensus(char**, n, min_cov, K, min_idt)
+    (consensus.py:110-117), including the eqv array."""
+    from falcon_b200 import binding
+    lib = binding.lib()
+    S = synth.make_set(30000, 3000, 20, seed=9, n_blocks=2)
+    for bi in range(2):
+        seqs = S.block_seqs(bi)
+        arr = (C.c_char_p * len(seqs))(*seqs)
+        p = lib.generate_consensus(arr, len(seqs), 4, 8, 0.70)
+        cns = C.string_at(p[0].sequence)
+        eqv = [C.cast(p[0].eff_cov, C.POINTER(C.c_int))[i] for i in range(len(cns))]
+        lib.free_consensus_data(p)
+        want, weqv = oracle.generate_consensus(seqs, 4, 0.70, want_eqv=True)
+        assert cns == want
+        assert eqv == weqv
+
+
+def test_waves_do_not_change_results(oracle):
+    """Splitting a call into many waves (tiny wave limits) must give identical output."""
+    from falcon_b200.binding import Engine
+    S = synth.make_set(60000, 4000, 25, seed=12, n_blocks=9)
+    e1 = Engine(0)
+    e1.upload_pool(S.pool)
+    a = e1.consensus_blocks([b.tolist() for b in S.blocks], 4, 0.70)
+    os.environ["FCX_WAVE_BLOCKS"] = "2"
+    try:
+        e2 = Engine(0)
+    finally:
+        del os.environ["FCX_WAVE_BLOCKS"]
+    e2.upload_pool(S.pool)
+    b = e2.consensus_blocks([x.tolist() for x in S.blocks], 4, 0.70)
+    assert a == b
+    assert e2.stats()["waves"] >= 4
+    for bi in (0, 8):
+        assert a[bi] == oracle.generate_consensus(S.block_seqs(bi), 4, 0.70)
+
+
+def test_full_size_properties(engine):
+    """At BASELINE size (15 kb reads, 50x) the oracle is too slow for the whole set; check
+    size-independent properties: determinism, order independence of blocks, and that the consensus
+    of each block is close to the seed's error-free template length."""
+    S = synth.make_set(400000, 15000, 50, seed=20, n_blocks=24, block_stride=40)
+    engine.upload_pool(S.pool)
+    blocks = [b.tolist() for b in S.blocks]
+    a = engine.consensus_blocks(blocks, 4, 0.70)
+    st = engine.stats()
+    b = engine.consensus_blocks(blocks, 4, 0.70)
+    assert a == b                                     # deterministic
+    perm = list(reversed(range(len(blocks))))
+    c = engine.consensus_blocks([blocks[i] for i in perm], 4, 0.70)
+    assert [c[perm.index(i)] for i in range(len(blocks))] == a   # blocks are independent
+    assert st["accepted"] > 0.9 * st["dp_pairs"]
+    import re
+    for cns in a:
+        runs = re.findall(b"[ACGT]+", cns)
+        assert runs and max(len(r) for r in runs) > 9000   # a 15 kb seed corrects to a long p-read
+
+
+def test_full_size_block_vs_oracle(engine, oracle):
+    S = synth.make_set(200000, 15000, 50, seed=21, n_blocks=2, block_stride=300)
+    engine.upload_pool(S.pool)
+    got = engine.consensus_blocks([b.tolist() for b in S.blocks], 4, 0.70)
+    for bi in range(len(S.blocks)):
+        assert got[bi] == oracle.generate_consensus(S.block_seqs(bi), 4, 0.70)
