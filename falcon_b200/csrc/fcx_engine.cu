@@ -56,8 +56,12 @@ struct fcx_ctx {
     std::vector<int32_t> h_len;
     DevBuf d_pool, d_ascii, d_aoff, d_woff, d_len, d_dirty;
     // wave buffers
-    DevBuf d_blocks, d_pairs, d_ranges, d_allocs, d_aln, d_ktab, d_kpos, d_trace, d_path, d_xam,
+    DevBuf d_blocks, d_pairs, d_ranges, d_allocs, d_aln, d_ktab, d_kpos, d_trace, d_path, d_xam, d_ent, d_M,
            d_recs, d_cov, d_lvl, d_acc, d_cns, d_eqv, d_cnsout;
+    DevBuf d_rlist;
+    int sm_count = 148;
+    bool profile = false;
+    double prof[8] = {0};
     HostBuf h_ranges, h_aln, h_cns, h_cnsout, h_stage, h_eqv;
     // results
     std::vector<char> out_bases;
@@ -70,7 +74,7 @@ struct fcx_ctx {
     uint64_t counters[FCX_C_COUNT] = {0};
     cudaEvent_t ev[8] = {nullptr};
     cudaEvent_t tev[2] = {nullptr, nullptr};
-    size_t arena_budget = (size_t)40 << 30;
+    size_t arena_budget = (size_t)110 << 30;
     uint32_t max_wave_blocks = 4096;
     uint32_t max_wave_pairs = 1u << 19;
 };
@@ -116,6 +120,8 @@ extern "C" int fcx_create(int device, fcx_ctx** out) {
     if (const char* s = getenv("FCX_ARENA_GB")) ctx->arena_budget = (size_t)atof(s) * ((size_t)1 << 30);
     if (const char* s = getenv("FCX_WAVE_BLOCKS")) ctx->max_wave_blocks = (uint32_t)atoi(s);
     if (const char* s = getenv("FCX_WAVE_PAIRS")) ctx->max_wave_pairs = (uint32_t)atoi(s);
+    if (const char* s = getenv("FCX_PROFILE")) ctx->profile = atoi(s) != 0;
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     // dynamic shared memory opt-in for k_range
     cudaFuncSetAttribute(k_range, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          RANGE_WARPS * RANGE_BINS * (int)sizeof(int));
@@ -129,7 +135,7 @@ extern "C" void fcx_destroy(fcx_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->d_pool, &ctx->d_ascii, &ctx->d_aoff, &ctx->d_woff, &ctx->d_len, &ctx->d_dirty,
                       &ctx->d_blocks, &ctx->d_pairs, &ctx->d_ranges, &ctx->d_allocs, &ctx->d_aln,
-                      &ctx->d_ktab, &ctx->d_kpos, &ctx->d_trace, &ctx->d_path, &ctx->d_xam, &ctx->d_recs,
+                      &ctx->d_ktab, &ctx->d_kpos, &ctx->d_trace, &ctx->d_path, &ctx->d_xam, &ctx->d_ent, &ctx->d_M, &ctx->d_rlist, &ctx->d_recs,
                       &ctx->d_cov, &ctx->d_lvl, &ctx->d_acc, &ctx->d_cns, &ctx->d_eqv, &ctx->d_cnsout};
     for (auto* b : bufs) b->release();
     HostBuf* hb[] = {&ctx->h_ranges, &ctx->h_aln, &ctx->h_cns, &ctx->h_cnsout, &ctx->h_stage, &ctx->h_eqv};
@@ -204,7 +210,7 @@ int run_wave(fcx_ctx* ctx, uint32_t b0, uint32_t b1, const uint32_t* block_off, 
              unsigned min_cov, double min_idt, uint64_t pair_base) {
     const uint32_t nb = b1 - b0;
     std::vector<BlockDesc> hb(nb);
-    uint64_t npairs64 = 0, kpos_total = 0, rec_total = 0, cns_total = 0, cov_total = 0;
+    uint64_t npairs64 = 0, kpos_total = 0, rec_total = 0, cns_total = 0, cov_total = 0, m_total = 0, tiles = 0;
     uint32_t max_np = 1;
     for (uint32_t b = 0; b < nb; b++) {
         uint32_t lo = block_off[b0 + b], hi = block_off[b0 + b + 1];
@@ -219,6 +225,9 @@ int run_wave(fcx_ctx* ctx, uint32_t b0, uint32_t b1, const uint32_t* block_off, 
         d.rec_off = rec_total; rec_total += d.rec_cap;
         d.cns_off = cns_total; cns_total += (uint64_t)d.slen * 2 + 8;
         d.cov_off = cov_total; cov_total += (uint64_t)d.slen + 8;
+        d.rb_pad = (d.n_pairs + 31u) & ~31u;
+        d.m_off = m_total; m_total += (uint64_t)d.rb_pad * (uint64_t)std::max(d.slen, 1);
+        d.tile_begin = (uint32_t)tiles; tiles += (uint64_t)((d.slen + 31) / 32) * (d.rb_pad / 32);
         npairs64 += d.n_pairs;
         max_np = std::max(max_np, d.n_pairs);
     }
@@ -241,13 +250,12 @@ int run_wave(fcx_ctx* ctx, uint32_t b0, uint32_t b1, const uint32_t* block_off, 
     CK(ctx->d_ktab.reserve((size_t)nb * KTAB * 4));
     CK(ctx->d_kpos.reserve(kpos_total * 4 + 16));
     CK(ctx->d_recs.reserve(rec_total * sizeof(CnsRec)));
-    CK(ctx->d_cov.reserve(cov_total * 2));
     CK(ctx->d_cns.reserve(cns_total));
     CK(ctx->d_eqv.reserve(cns_total * 4));
     CK(ctx->d_cnsout.reserve(nb * sizeof(CnsOut)));
     const uint32_t cns_grid = (nb + CNS_WARPS - 1) / CNS_WARPS;
     CK(ctx->d_lvl.reserve((size_t)cns_grid * CNS_WARPS * 4 * LVL * 4));
-    CK(ctx->d_acc.reserve((size_t)cns_grid * CNS_WARPS * max_np * 4));
+    CK(ctx->d_acc.reserve((size_t)cns_grid * CNS_WARPS * max_np * sizeof(ReadMeta)));
     CK(ctx->h_ranges.reserve((size_t)std::max(np, 1u) * sizeof(PairRange)));
     CK(ctx->h_aln.reserve((size_t)std::max(np, 1u) * sizeof(PairAln)));
     CK(ctx->h_cns.reserve(cns_total));
@@ -266,9 +274,11 @@ int run_wave(fcx_ctx* ctx, uint32_t b0, uint32_t b1, const uint32_t* block_off, 
     ctx->counters[FCX_C_KERNEL_LAUNCHES] += 1;
     // ---- range
     if (np) {
-        k_range<<<(np + RANGE_WARPS - 1) / RANGE_WARPS, RANGE_WARPS * 32, RANGE_WARPS * RANGE_BINS * sizeof(int), st>>>(
+        const unsigned rgrid = std::min<unsigned>((np + RANGE_WARPS - 1) / RANGE_WARPS, (unsigned)ctx->sm_count * 3u);
+        CK(ctx->d_rlist.reserve((size_t)rgrid * RANGE_WARPS * RANGE_LIST_CAP * sizeof(int2)));
+        k_range<<<rgrid, RANGE_WARPS * 32, RANGE_WARPS * RANGE_BINS * sizeof(int), st>>>(
             ctx->d_blocks.as<BlockDesc>(), ctx->d_pairs.as<PairDesc>(), np, pool, ctx->d_ktab.as<uint32_t>(),
-            ctx->d_kpos.as<uint32_t>(), ctx->d_ranges.as<PairRange>());
+            ctx->d_kpos.as<uint32_t>(), ctx->d_rlist.as<int2>(), ctx->d_ranges.as<PairRange>());
         CK(cudaGetLastError());
         ctx->counters[FCX_C_KERNEL_LAUNCHES] += 1;
         CK(cudaMemcpyAsync(ctx->h_ranges.p, ctx->d_ranges.p, (size_t)np * sizeof(PairRange), cudaMemcpyDeviceToHost, st));
@@ -290,6 +300,8 @@ int run_wave(fcx_ctx* ctx, uint32_t b0, uint32_t b1, const uint32_t* block_off, 
     }
     CK(ctx->d_trace.reserve(trace_recs * TRACE_REC_WORDS * 4 + 64));
     CK(ctx->d_xam.reserve(xam_n * 4 + 64));
+    CK(ctx->d_ent.reserve(xam_n * 4 + 64));
+    CK(ctx->d_M.reserve(m_total * 4 + 64));
     CK(ctx->d_path.reserve(path_w * 4 + 64));
     if (np) CK(cudaMemcpyAsync(ctx->d_allocs.p, ha.data(), (size_t)np * sizeof(PairAlloc), cudaMemcpyHostToDevice, st));
     // ---- DP
@@ -307,17 +319,28 @@ int run_wave(fcx_ctx* ctx, uint32_t b0, uint32_t b1, const uint32_t* block_off, 
         k_traceback<<<(np + 127) / 128, 128, 0, st>>>(
             ctx->d_blocks.as<BlockDesc>(), ctx->d_pairs.as<PairDesc>(), ctx->d_ranges.as<PairRange>(),
             ctx->d_allocs.as<PairAlloc>(), np, pool, ctx->d_trace.as<uint32_t>(), ctx->d_path.as<uint32_t>(),
-            ctx->d_xam.as<uint32_t>(), ctx->d_aln.as<PairAln>());
+            ctx->d_xam.as<uint32_t>(), ctx->d_ent.as<uint32_t>(), ctx->d_aln.as<PairAln>());
+        CK(cudaGetLastError());
+        ctx->counters[FCX_C_KERNEL_LAUNCHES] += 1;
+    }
+    if (tiles) {
+        k_transpose<<<(unsigned)((tiles + TR_WARPS - 1) / TR_WARPS), TR_WARPS * 32, 0, st>>>(
+            ctx->d_blocks.as<BlockDesc>(), nb, (uint32_t)tiles, ctx->d_ranges.as<PairRange>(),
+            ctx->d_allocs.as<PairAlloc>(), ctx->d_aln.as<PairAln>(), ctx->d_ent.as<uint32_t>(), ctx->d_M.as<uint32_t>());
         CK(cudaGetLastError());
         ctx->counters[FCX_C_KERNEL_LAUNCHES] += 1;
     }
     CK(cudaEventRecord(ctx->ev[5], st));
     // ---- consensus
-    k_consensus<<<cns_grid, CNS_WARPS * 32, 0, st>>>(
-        ctx->d_blocks.as<BlockDesc>(), nb, ctx->d_pairs.as<PairDesc>(), ctx->d_ranges.as<PairRange>(),
-        ctx->d_allocs.as<PairAlloc>(), ctx->d_aln.as<PairAln>(), pool, ctx->d_xam.as<uint32_t>(),
-        ctx->d_recs.as<CnsRec>(), ctx->d_cov.as<uint16_t>(), ctx->d_lvl.as<int32_t>(), ctx->d_acc.as<uint32_t>(),
-        (uint64_t)max_np, ctx->d_cns.as<char>(), ctx->d_eqv.as<int32_t>(), min_cov, ctx->d_cnsout.as<CnsOut>());
+    {
+        auto kfn = ctx->profile ? k_consensus<true> : k_consensus<false>;
+        kfn<<<cns_grid, CNS_WARPS * 32, 0, st>>>(
+            ctx->d_blocks.as<BlockDesc>(), nb, ctx->d_pairs.as<PairDesc>(), ctx->d_ranges.as<PairRange>(),
+            ctx->d_allocs.as<PairAlloc>(), ctx->d_aln.as<PairAln>(), pool, ctx->d_xam.as<uint32_t>(),
+            ctx->d_M.as<uint32_t>(), ctx->d_recs.as<CnsRec>(), ctx->d_lvl.as<int32_t>(),
+            ctx->d_acc.as<ReadMeta>(), (uint64_t)max_np, ctx->d_cns.as<char>(), ctx->d_eqv.as<int32_t>(), min_cov,
+            ctx->d_cnsout.as<CnsOut>());
+    }
     CK(cudaGetLastError());
     ctx->counters[FCX_C_KERNEL_LAUNCHES] += 1;
     CK(cudaEventRecord(ctx->ev[6], st));
@@ -340,6 +363,9 @@ int run_wave(fcx_ctx* ctx, uint32_t b0, uint32_t b1, const uint32_t* block_off, 
                      co[b].err, b0 + b);
             ctx->err = buf; return 3;
         }
+        ctx->prof[0] += co[b].deep_positions; ctx->prof[1] += co[b].positions;
+        ctx->prof[2] += (double)co[b].cyc_vote; ctx->prof[3] += (double)co[b].cyc_dp;
+        ctx->prof[4] += (double)co[b].cyc_generic; ctx->prof[5] += (double)co[b].cyc_backtrack;
         ctx->out_bases.insert(ctx->out_bases.end(), hc + hb[b].cns_off, hc + hb[b].cns_off + co[b].len);
         ctx->out_off.push_back(ctx->out_bases.size());
         if (ctx->want_eqv) {
@@ -387,8 +413,10 @@ extern "C" int fcx_consensus_blocks(fcx_ctx* ctx, uint32_t n_blocks, const uint3
     ctx->out_bases.clear(); ctx->out_off.clear(); ctx->out_off.push_back(0); ctx->pair_info.clear();
     ctx->out_eqv.clear();
     memset(ctx->times, 0, sizeof ctx->times); memset(ctx->counters, 0, sizeof ctx->counters);
+    memset(ctx->prof, 0, sizeof ctx->prof);
     for (uint32_t b = 0; b < n_blocks; b++) {
         if (block_off[b + 1] <= block_off[b]) { ctx->err = "empty block (a block needs at least the seed)"; return 1; }
+        if (block_off[b + 1] - block_off[b] > 65000) { ctx->err = "more than 65000 reads in one block"; return 1; }
         for (uint32_t i = block_off[b]; i < block_off[b + 1]; i++)
             if (read_ids[i] >= ctx->n_reads) { ctx->err = "read id outside the uploaded pool"; return 1; }
     }
@@ -399,10 +427,10 @@ extern "C" int fcx_consensus_blocks(fcx_ctx* ctx, uint32_t n_blocks, const uint3
         while (e < n_blocks) {
             uint32_t lo = block_off[e], hi = block_off[e + 1];
             int slen = ctx->h_len[read_ids[lo]];
-            double bb = (double)KTAB * 4 + (double)slen * (4 + 8 * 12 + 2 * 5 + 2);
+            double bb = (double)KTAB * 4 + (double)slen * (4 + 8 * 12 + 2 * 5 + 2) + 4.0 * slen * (((hi - lo - 1) + 31) & ~31u);
             for (uint32_t i = lo + 1; i < hi; i++) {
                 int rl = ctx->h_len[read_ids[i]];
-                bb += 0.3 * (rl + slen) * 36.0 + 4.0 * (slen + 2) + 128;
+                bb += 0.3 * (rl + slen) * 36.0 + 8.0 * (slen + 2) + 128;
             }
             if (e > b && (bytes + bb > (double)ctx->arena_budget || pairs + (hi - lo - 1) > ctx->max_wave_pairs ||
                           e - b >= ctx->max_wave_blocks)) break;
@@ -429,6 +457,8 @@ extern "C" int fcx_last_stats(fcx_ctx* ctx, double* times_ms, uint64_t* counters
     if (counters) memcpy(counters, ctx->counters, sizeof ctx->counters);
     return 0;
 }
+
+extern "C" int fcx_internal_profile(fcx_ctx* ctx, double* out8) { memcpy(out8, ctx->prof, sizeof ctx->prof); return 0; }
 
 // CUDA-event stopwatch on the engine's stream (bench.py brackets its timed region with it)
 extern "C" int fcx_timer_start(fcx_ctx* ctx) {

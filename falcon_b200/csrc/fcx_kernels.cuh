@@ -38,6 +38,9 @@ struct BlockDesc {
     uint32_t n_pairs;     // n_seq - 1
     int32_t  slen;        // seed length
     uint32_t rec_cap;     // capacity (records)
+    uint64_t m_off;       // offset (entries) of this block's position-major pile-up matrix
+    uint32_t rb_pad;      // row length of the matrix: n_pairs rounded up to 32
+    uint32_t tile_begin;  // first 32x32 transpose tile of this block
 };
 
 struct PairDesc {
@@ -173,21 +176,11 @@ __global__ void __launch_bounds__(256) k_index(const BlockDesc* __restrict__ blo
 constexpr int RANGE_WARPS = 4;
 constexpr int RANGE_BINS = 4224;   // >= (99999 + 99999) / 48 + 1
 
-__global__ void __launch_bounds__(RANGE_WARPS * 32)
-k_range(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs, uint32_t n_pairs,
-        const uint32_t* __restrict__ pool, const uint32_t* __restrict__ ktab,
-        const uint32_t* __restrict__ kpos_arena, PairRange* __restrict__ out) {
-    extern __shared__ int s_hist_all[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const uint32_t p = blockIdx.x * RANGE_WARPS + wib;
-    if (p >= n_pairs) return;
-    int* hist = s_hist_all + wib * RANGE_BINS;
-    const PairDesc pd = pairs[p];
-    const BlockDesc bd = blocks[pd.block];
-    const uint32_t* read = pool + pd.read_woff;
-    const uint32_t* tab = ktab + (size_t)pd.block * KTAB;
-    const uint32_t* kpos = kpos_arena + bd.kpos_off;
-    const int nq = pd.rlen > KMER ? (pd.rlen - KMER + 3) / 4 : 0;   // i = 0,4,.. < rlen-K
+// Slow path (match list does not fit the per-warp scratch): every pass re-walks the buckets.
+__device__ void range_pair_slow(const uint32_t* __restrict__ read, const uint32_t* __restrict__ tab,
+                                const uint32_t* __restrict__ kpos, const int nq, int* hist, const int lane,
+                                PairRange* __restrict__ outp) {
+    PairRange* out = outp; const int p = 0;
     PairRange r; r.s1 = r.e1 = r.s2 = r.e2 = 0; r.n_match = 0; r.pass = 0;
 
     // ---- pass A
@@ -307,6 +300,133 @@ k_range(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs
     if (lane == 0) out[p] = r;
 }
 
+
+// Fast path: the match list (query position ascending, seed position ascending -- the order of
+// kmer_lookup.c:252-283) is materialised once into a per-warp global scratch, then the histogram,
+// arg-max and Kadane passes stream over it with coalesced loads.  Persistent warps: each warp owns
+// one scratch slot and loops over pairs.
+constexpr int RANGE_LIST_CAP = 16384;
+
+__global__ void __launch_bounds__(RANGE_WARPS * 32)
+k_range(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs, uint32_t n_pairs,
+        const uint32_t* __restrict__ pool, const uint32_t* __restrict__ ktab,
+        const uint32_t* __restrict__ kpos_arena, int2* __restrict__ list_scratch,
+        PairRange* __restrict__ out) {
+    extern __shared__ int s_hist_all[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    int* hist = s_hist_all + wib * RANGE_BINS;
+    const uint32_t gw = blockIdx.x * RANGE_WARPS + wib, nw = gridDim.x * RANGE_WARPS;
+    int2* list = list_scratch + (size_t)gw * RANGE_LIST_CAP;
+    const unsigned lt = lanemask_lt();
+    for (uint32_t p = gw; p < n_pairs; p += nw) {
+        const PairDesc pd = pairs[p];
+        const BlockDesc bd = blocks[pd.block];
+        const uint32_t* read = pool + pd.read_woff;
+        const uint32_t* tab = ktab + (size_t)pd.block * KTAB;
+        const uint32_t* kpos = kpos_arena + bd.kpos_off;
+        const int nq = pd.rlen > KMER ? (pd.rlen - KMER + 3) / 4 : 0;   // i = 0,4,.. < rlen-K
+        PairRange r; r.s1 = r.e1 = r.s2 = r.e2 = 0; r.n_match = 0; r.pass = 0;
+        // ---- materialise the match list
+        int n = 0, dmin = INT_MAX, dmax = INT_MIN; bool overflow = false;
+        for (int it0 = 0; it0 < nq; it0 += 32) {
+            const int it = it0 + lane, i = it * 4;
+            uint32_t s = 0, e = 0;
+            if (it < nq) {
+                const uint32_t kid = fetch16(read, i) & 0xffffu;
+                s = kid ? __ldg(tab + kid - 1) : 0u; e = __ldg(tab + kid);
+            }
+            const int c = (int)(e - s);
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
+            const int total = __shfl_sync(FULL, incl, 31);
+            if (n + total > RANGE_LIST_CAP) { overflow = true; break; }
+            int w = n + incl - c;
+            for (uint32_t j = s; j < e; j++, w++) {
+                const int t = (int)__ldg(kpos + j);
+                list[w] = make_int2(i, t);
+                dmin = min(dmin, i - t); dmax = max(dmax, i - t);
+            }
+            n += total;
+        }
+        if (overflow) { __syncwarp(); range_pair_slow(read, tab, kpos, nq, hist, lane, out + p); __syncwarp(); continue; }
+        r.n_match = n;
+        if (n == 0) { if (lane == 0) out[p] = r; continue; }
+        dmin = __reduce_min_sync(FULL, dmin); dmax = __reduce_max_sync(FULL, dmax);
+        const int nbin = (dmax - dmin) / BIN_SIZE + 1;
+        for (int b = lane; b < nbin; b += 32) hist[b] = 0;
+        __syncwarp();      // also orders the list writes before the reads below
+        // ---- histogram (kmer_lookup.c:346-355)
+        for (int e0 = 0; e0 < n; e0 += 32) {
+            const int e = e0 + lane;
+            if (e < n) { const int2 m = list[e]; atomicAdd(&hist[(m.x - m.y - dmin) / BIN_SIZE], 1); }
+        }
+        __syncwarp();
+        int top = 0;
+        for (int b = lane; b < nbin; b += 32) top = max(top, hist[b]);
+        top = __reduce_max_sync(FULL, top);
+        if (top <= COUNT_TH) { if (lane == 0) out[p] = r; __syncwarp(); continue; }
+        // ---- arg-max bin = bin of the first match whose bin holds `top` (:357-366)
+        int top_bin = -1;
+        for (int e0 = 0; e0 < n && top_bin < 0; e0 += 32) {
+            const int e = e0 + lane; int mybin = -1;
+            if (e < n) { const int2 m = list[e]; const int b = (m.x - m.y - dmin) / BIN_SIZE; if (hist[b] == top) mybin = b; }
+            const unsigned bal = __ballot_sync(FULL, mybin >= 0);
+            if (bal) top_bin = __shfl_sync(FULL, mybin, __ffs(bal) - 1);
+        }
+        // ---- kept matches + Kadane scan in closed form (:369-411), see the note above
+        int idx_base = 0;
+        bool have_min = false; int c_min = 0, c_mq = 0, c_mt = 0;
+        int best = 0, bs1 = 0, bs2 = 0, be1 = 0, be2 = 0;
+        bool first_set = false; int q0 = 0, t0 = 0;
+        for (int e0 = 0; e0 < n; e0 += 32) {
+            const int e = e0 + lane;
+            bool keep = false; int qi = 0, ti = 0;
+            if (e < n) {
+                const int2 m = list[e]; qi = m.x; ti = m.y;
+                const int b = (qi - ti - dmin) / BIN_SIZE;
+                keep = abs(b - top_bin) <= 5 && hist[b] > COUNT_TH;
+            }
+            const unsigned kb = __ballot_sync(FULL, keep);
+            if (!kb) continue;
+            const int excl = __popc(kb & lt), total = __popc(kb);
+            if (!first_set) { const int fl = __ffs(kb) - 1; q0 = __shfl_sync(FULL, qi, fl); t0 = __shfl_sync(FULL, ti, fl); first_set = true; }
+            int sv = keep ? 32 * (idx_base + excl) - qi : INT_MAX;      // fits: idx < 16384, q < 100000
+            int src = lane;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int ov = __shfl_up_sync(FULL, sv, o), os = __shfl_up_sync(FULL, src, o);
+                if (lane >= o && ov <= sv) { sv = ov; src = os; }        // earlier lane wins ties
+            }
+            const bool from_carry = have_min && c_min <= sv;
+            const int mval = from_carry ? c_min : sv;
+            int sq = __shfl_sync(FULL, qi, src), st = __shfl_sync(FULL, ti, src);
+            if (from_carry) { sq = c_mq; st = c_mt; }
+            const int cval = keep ? 32 * (idx_base + excl) - qi - mval : -1;
+            const int cmax = __reduce_max_sync(FULL, cval);
+            if (cmax > best) {
+                const unsigned who = __ballot_sync(FULL, cval == cmax);
+                const int wl = __ffs(who) - 1;
+                best = cmax;
+                be1 = __shfl_sync(FULL, qi, wl); be2 = __shfl_sync(FULL, ti, wl);
+                bs1 = __shfl_sync(FULL, sq, wl); bs2 = __shfl_sync(FULL, st, wl);
+            }
+            const int lv = __shfl_sync(FULL, mval, 31), lq = __shfl_sync(FULL, sq, 31), ltt = __shfl_sync(FULL, st, 31);
+            if (lv != INT_MAX) { have_min = true; c_min = lv; c_mq = lq; c_mt = ltt; }
+            idx_base += total;
+        }
+        if (idx_base > 1) {
+            if (best > 0) { r.s1 = bs1; r.s2 = bs2; r.e1 = be1; r.e2 = be2; }
+            else { r.s1 = r.e1 = q0; r.s2 = r.e2 = t0; }
+        }
+        // span filters, falcon.c:612-619 (double arithmetic kept as written there)
+        const int sp1 = r.e1 - r.s1, sp2 = r.e2 - r.s2;
+        r.pass = !(sp1 < 100 || sp2 < 100 || abs(sp1 - sp2) > (int)(0.5 * 0.10 * (sp1 + sp2)));
+        if (lane == 0) out[p] = r;
+        __syncwarp();
+    }
+}
+
 // ------------------------------------------------------------------------------ k_dp
 // One warp per pair: furthest-reaching banded O(ND) forward pass (DW_banded.c:149-258).
 // Lanes own diagonals k = min_k + 2*lane (+64 per extra band chunk).  V lives in a 512-entry
@@ -314,22 +434,59 @@ k_range(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs
 // DW_banded.c:213 only ever reads the opposite parity, written at d-1).  Per step one 32-byte
 // trace record is written: [min_k, ballot words of "came from k+1"].  x2/y2 are NOT stored; the
 // traceback kernel re-walks the path and recomputes the snakes.
+// Steps whose band holds <= 64 cells (virtually all) run a register-resident fast path with one
+// or two cells per lane; wider bands (<= 151 cells) take the generic chunk loop.
 constexpr int DP_WARPS = 8;
 constexpr int VRING = 512;
 
-__device__ __forceinline__ int snake(const uint32_t* __restrict__ q, const uint32_t* __restrict__ t,
-                                     int qs, int ts, int q_len, int t_len, int& x, int& y) {
-    int adv = 0;
+__device__ __forceinline__ void snake(const uint32_t* __restrict__ q, const uint32_t* __restrict__ t,
+                                      int qs, int ts, int q_len, int t_len, int& x, int& y) {
     for (;;) {
         int rem = min(q_len - x, t_len - y);
         if (rem <= 0) break;
         uint32_t diff = fetch16(q, qs + x) ^ fetch16(t, ts + y);
         int n = diff ? (__ffs(diff) - 1) >> 1 : 16;
         n = min(n, rem);
-        x += n; y += n; adv += n;
+        x += n; y += n;
         if (n < 16) break;
     }
-    return adv;
+}
+
+struct DpCell { int x, y; bool up; };
+
+// predecessor choice of one cell (DW_banded.c:190-197); inactive lanes get a harmless (0,0)
+__device__ __forceinline__ DpCell dp_pick(const int* V, int d, int k, int min_k, int max_k, bool act) {
+    DpCell c; c.up = false; c.x = 0; c.y = 0;
+    if (d == 0) { c.up = act; }                             // V[k+1] is calloc'd 0
+    else {
+        const int vm = V[(k - 1) & (VRING - 1)], vp = V[(k + 1) & (VRING - 1)];
+        const bool up = (k == min_k) || (k != max_k && vm < vp);
+        c.up = act && up;
+        c.x = act ? (up ? vp : vm + 1) : 0;
+        c.y = act ? c.x - k : 0;
+    }
+    return c;
+}
+
+// one 16-base compare (DW_banded.c:203-206), straight-line so that all lanes stay converged;
+// returns the advance (16 = all compared bases matched and neither end was reached: go on)
+__device__ __forceinline__ int snake16(const uint32_t* __restrict__ q, const uint32_t* __restrict__ t,
+                                       int qs, int ts, int q_len, int t_len, bool act, int& x, int& y) {
+    const int rem = act ? max(min(q_len - x, t_len - y), 0) : 0;
+    const uint32_t diff = fetch16(q, qs + x) ^ fetch16(t, ts + y);
+    int n = diff ? (__ffs(diff) - 1) >> 1 : 16;
+    n = min(n, rem);
+    x += n; y += n;
+    return n;
+}
+
+// full DP cell for the generic (wide band) path
+__device__ __forceinline__ DpCell dp_cell(const int* V, int d, int k, int min_k, int max_k,
+                                          const uint32_t* __restrict__ q, const uint32_t* __restrict__ t,
+                                          int qs, int ts, int q_len, int t_len) {
+    DpCell c = dp_pick(V, d, k, min_k, max_k, true);
+    snake(q, t, qs, ts, q_len, t_len, c.x, c.y);
+    return c;
 }
 
 __global__ void __launch_bounds__(DP_WARPS * 32)
@@ -359,35 +516,70 @@ k_dp(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs,
     for (int d = 0; d < max_d; d++) {
         if (max_k - min_k > band_size) break;                  // :184-186
         const int ncell = ((max_k - min_k) >> 1) + 1;
-        const int nch = (ncell + 31) >> 5;
         uint32_t* rec = trace + (size_t)d * TRACE_REC_WORDS;
+        if (ncell <= 64) {
+            // ------------------------------------------------ fast step: <= 2 cells per lane
+            const bool two = ncell > 32;
+            const int k0 = min_k + 2 * lane, k1 = k0 + 64;
+            const bool a0 = k0 <= max_k, a1 = two && k1 <= max_k;
+            DpCell c0 = dp_pick(V, d, k0, min_k, max_k, a0), c1;
+            c1.x = c1.y = 0; c1.up = false;
+            int n0 = snake16(q, t, qs, ts, q_len, t_len, a0, c0.x, c0.y), n1 = 0;
+            if (two) {
+                c1 = dp_pick(V, d, k1, min_k, max_k, a1);
+                n1 = snake16(q, t, qs, ts, q_len, t_len, a1, c1.x, c1.y);
+            }
+            while (__ballot_sync(FULL, n0 == 16 || n1 == 16)) {      // long snakes: rare
+                if (n0 == 16) n0 = snake16(q, t, qs, ts, q_len, t_len, true, c0.x, c0.y);
+                if (n1 == 16) n1 = snake16(q, t, qs, ts, q_len, t_len, true, c1.x, c1.y);
+            }
+            const unsigned up0 = __ballot_sync(FULL, c0.up);
+            const unsigned up1 = two ? __ballot_sync(FULL, c1.up) : 0u;
+            if (lane < 3) rec[lane] = lane == 0 ? (uint32_t)min_k : (lane == 1 ? up0 : up1);
+            const unsigned fin0 = __ballot_sync(FULL, a0 && (c0.x >= q_len || c0.y >= t_len));     // :220
+            const unsigned fin1 = two ? __ballot_sync(FULL, a1 && (c1.x >= q_len || c1.y >= t_len)) : 0u;
+            if (fin0 | fin1) {                                  // first k in ascending order wins
+                const int fl = fin0 ? __ffs(fin0) - 1 : __ffs(fin1) - 1;
+                aligned = true; end_d = d; end_k = (fin0 ? k0 : k1) - 2 * lane + 2 * fl;
+                end_x = __shfl_sync(FULL, fin0 ? c0.x : c1.x, fl);
+                end_y = __shfl_sync(FULL, fin0 ? c0.y : c1.y, fl);
+                cells += (fin0 ? 0 : 32) + fl + 1;
+                break;
+            }
+            cells += ncell;
+            if (a0) V[k0 & (VRING - 1)] = c0.x;
+            if (a1) V[k1 & (VRING - 1)] = c1.x;
+            const int u0 = a0 ? c0.x + c0.y : INT_MIN, u1 = a1 ? c1.x + c1.y : INT_MIN;
+            best_m = max(best_m, __reduce_max_sync(FULL, max(u0, u1)));
+            const int thr = best_m - BAND_TOL;                  // band update, :227-243
+            const unsigned ok0 = __ballot_sync(FULL, u0 >= thr);
+            const unsigned ok1 = two ? __ballot_sync(FULL, u1 >= thr) : 0u;
+            const int nmin = ok0 ? min_k + 2 * (__ffs(ok0) - 1) : min_k + 64 + 2 * (__ffs(ok1) - 1);
+            const int nmax = ok1 ? min_k + 64 + 2 * (31 - __clz(ok1)) : min_k + 2 * (31 - __clz(ok0));
+            max_k = nmax + 1; min_k = nmin - 1;
+            __syncwarp();
+            continue;
+        }
+        // ---------------------------------------------------- generic step: up to 151 cells
+        const int nch = (ncell + 31) >> 5;
         if (lane == 0) rec[0] = (uint32_t)min_k;
         int step_best = best_m;
         for (int c = 0; c < nch; c++) {
             const int k = min_k + 2 * (lane + 32 * c);
             const bool act = k <= max_k;
-            bool up = false; int x = 0, y = 0;
-            if (act) {
-                if (d == 0) { up = true; x = 0; }              // V[k+1] is calloc'd 0
-                else {
-                    int vm = V[(k - 1) & (VRING - 1)], vp = V[(k + 1) & (VRING - 1)];
-                    up = (k == min_k) || (k != max_k && vm < vp);   // :190
-                    x = up ? vp : vm + 1;
-                }
-                y = x - k;
-                snake(q, t, qs, ts, q_len, t_len, x, y);
-            }
-            unsigned upb = __ballot_sync(FULL, act && up);
+            DpCell cc; cc.x = cc.y = 0; cc.up = false;
+            if (act) cc = dp_cell(V, d, k, min_k, max_k, q, t, qs, ts, q_len, t_len);
+            unsigned upb = __ballot_sync(FULL, act && cc.up);
             if (lane == 0) rec[1 + c] = upb;
-            const bool fin = act && (x >= q_len || y >= t_len);     // :220
+            const bool fin = act && (cc.x >= q_len || cc.y >= t_len);
             unsigned finb = __ballot_sync(FULL, fin);
-            if (act) V[k & (VRING - 1)] = x;
-            int u = act ? x + y : INT_MIN;
+            if (act) V[k & (VRING - 1)] = cc.x;
+            int u = act ? cc.x + cc.y : INT_MIN;
             step_best = max(step_best, __reduce_max_sync(FULL, u));
-            if (finb) {                                         // first k in ascending order wins
+            if (finb) {
                 int fl = __ffs(finb) - 1;
                 aligned = true; end_d = d; end_k = min_k + 2 * (fl + 32 * c);
-                end_x = __shfl_sync(FULL, x, fl); end_y = __shfl_sync(FULL, y, fl);
+                end_x = __shfl_sync(FULL, cc.x, fl); end_y = __shfl_sync(FULL, cc.y, fl);
                 cells += fl + 1;
                 break;
             }
@@ -396,7 +588,6 @@ k_dp(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs,
         if (aligned) break;
         best_m = step_best;
         __syncwarp();
-        // band update, :227-243
         int nmin = INT_MAX, nmax = INT_MIN;
         const int thr = best_m - BAND_TOL;
         for (int c = 0; c < nch; c++) {
@@ -425,18 +616,26 @@ k_dp(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs,
 // ------------------------------------------------------------------------------ k_traceback
 // One thread per accepted pair.  (1) walk the trace records backwards collecting the direction
 // bit of every step of the optimal path (DW_banded.c:264-277); (2) replay the path forwards,
-// recomputing the snakes, and emit per target position y the record
-//        xam[y] = (x << 1) | is_match      x = query index when target base y is consumed,
-// plus the sentinel xam[t_e] = q_e << 1.  This is get_align_tags (falcon.c:106-162) in closed
-// form: the delta-0 tag of column y carries the seed base (match) or '-', and the insertion tags
-// delta = 1..n are the query bases x+is_match .. x_next-1.  The reference stops tagging at the
-// first column whose delta reaches 255 (falcon.c:138,150-152): t_cnt is cut there and the
-// sentinel rewritten so that exactly 254 insertion tags remain.
+// recomputing the snakes, and emit per target position y two records:
+//        xam[y] = (x << 1) | is_match      x = query index when target base y is consumed
+//                                          (sentinel xam[t_cnt] = x_end << 1)
+//        ent[y] = VALID | is_match<<30 | n_ins<<22 | first 11 inserted bases (2 bits each)
+// This is get_align_tags (falcon.c:106-162) in closed form: the delta-0 tag of column y carries
+// the seed base (match) or '-', and the insertion tags delta = 1..n_ins are the query bases
+// x+is_match .. x_next-1.  The reference stops tagging at the first column whose delta reaches 255
+// (falcon.c:138,150-152): t_cnt is cut there and exactly 254 insertion tags remain.
+constexpr uint32_t ENT_VALID = 0x80000000u;
+constexpr uint32_t ENT_MATCH = 0x40000000u;
+constexpr int ENT_INS_INLINE = 11;
+__device__ __forceinline__ int ent_nins(uint32_t e) { return (int)((e >> 22) & 0xffu); }
+__device__ __forceinline__ int ent_ins(uint32_t e, int k) { return (int)((e >> (2 * k)) & 3u); }
+
 __global__ void k_traceback(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs,
                             const PairRange* __restrict__ ranges, const PairAlloc* __restrict__ allocs,
                             uint32_t n_pairs, const uint32_t* __restrict__ pool,
                             const uint32_t* __restrict__ trace_arena, uint32_t* __restrict__ path_arena,
-                            uint32_t* __restrict__ xam_arena, PairAln* __restrict__ aln) {
+                            uint32_t* __restrict__ xam_arena, uint32_t* __restrict__ ent_arena,
+                            PairAln* __restrict__ aln) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_pairs) return;
     PairAln a = aln[p];
@@ -450,6 +649,7 @@ __global__ void k_traceback(const BlockDesc* __restrict__ blocks, const PairDesc
     const uint32_t* trace = trace_arena + al.trace_off * TRACE_REC_WORDS;
     uint32_t* path = path_arena + al.path_off;
     uint32_t* xam = xam_arena + al.xam_off;
+    uint32_t* ent = ent_arena + al.xam_off;
     const int D = a.dist;
     // (1) backwards: bit d of path = step d came from k+1 (a target-only column)
     int k = a.k_end;
@@ -464,16 +664,21 @@ __global__ void k_traceback(const BlockDesc* __restrict__ blocks, const PairDesc
     }
     // (2) forwards
     int x = 0, y = 0, run = 0, t_cnt = -1, n_match_cols = 0;
+    uint32_t pend = 0; int pend_y = -1;          // entry of the last target column, still open
     uint32_t pw = 0;
     for (int d = 0; d <= D; d++) {
         if (d > 0) {
             if ((d & 31) == 0 || d == 1) pw = path[d >> 5];
-            if ((pw >> (d & 31)) & 1u) { xam[y] = (uint32_t)x << 1; y++; run = 0; }   // target-only column
-            else {
+            if ((pw >> (d & 31)) & 1u) {              // target-only column
+                if (pend_y >= 0) ent[pend_y] = pend | ((uint32_t)run << 22);
+                xam[y] = (uint32_t)x << 1; pend = ENT_VALID; pend_y = y; y++; run = 0;
+            } else {                                  // query-only column
+                if (run < ENT_INS_INLINE) pend |= (uint32_t)base_at(q, qs + x) << (2 * run);
                 x++; run++;
                 if (run == 255) {            // the 255th consecutive query-only column: tags stop before it
                     t_cnt = y;               // target positions 0..y-1 carry tags
                     xam[y] = (uint32_t)(x - 1) << 1;   // keeps n_ins(y-1) == 254
+                    run = 254;
                     break;
                 }
             }
@@ -485,12 +690,17 @@ __global__ void k_traceback(const BlockDesc* __restrict__ blocks, const PairDesc
             uint32_t diff = fetch16(q, qs + x) ^ fetch16(t, ts + y);
             int n = diff ? (__ffs(diff) - 1) >> 1 : 16;
             n = min(n, rem);
-            for (int j = 0; j < n; j++) xam[y + j] = ((uint32_t)(x + j) << 1) | 1u;
+            if (n > 0) {
+                if (pend_y >= 0) ent[pend_y] = pend | ((uint32_t)run << 22);
+                for (int j = 0; j < n; j++) xam[y + j] = ((uint32_t)(x + j) << 1) | 1u;
+                for (int j = 0; j + 1 < n; j++) ent[y + j] = ENT_VALID | ENT_MATCH;
+                pend = ENT_VALID | ENT_MATCH; pend_y = y + n - 1; run = 0;
+            }
             x += n; y += n; n_match_cols += n;
-            if (n > 0) run = 0;
             if (n < 16) break;
         }
     }
+    if (pend_y >= 0) ent[pend_y] = pend | ((uint32_t)run << 22);
     if (t_cnt < 0) { t_cnt = y; xam[y] = (uint32_t)x << 1; }
     a.t_cnt = t_cnt;
     // tagged columns = target columns + query-only columns among them
@@ -498,238 +708,57 @@ __global__ void k_traceback(const BlockDesc* __restrict__ blocks, const PairDesc
     aln[p] = a;
 }
 
-// ------------------------------------------------------------------------------ k_consensus
-// One warp per seed block, serial over target positions (the longest-path DP of
-// falcon.c:405-475 is serial in t_pos).  Per position i:
-//   vote   every accepted read covering i contributes its delta-0 tag and its insertion tags
-//          (falcon.c:350-382); identical links are merged into a per-position link list in
-//          first-appearance order (= ascending accepted-read index, update_col falcon.c:232-263);
-//   DP     for delta j = 0..max_delta, base kk = 0..4: best link by strict '>' in list order,
-//          score = pred + count - 0.5*coverage kept as an exact integer (x2); columns whose best
-//          stays <= -1 keep score -1 and best_p = (0,0,0) as in the reference;
-//   global best by strict '>' in (i, j, kk) order, remembering the best LINK INDEX (quirk).
-// Then the backtrack of falcon.c:479-542 over the stored column records.
-struct CnsRec { int32_t pred; int32_t info; int32_t score2; };   // info = (t_pos << 3) | base
-constexpr int CNS_WARPS = 4;
-constexpr int LINK_CAP = 512;         // distinct (delta, base, link) entries per position
-constexpr int LVL = 255 * 5;
-
-struct CnsOut { int32_t len; int32_t err; };
-
-__global__ void __launch_bounds__(CNS_WARPS * 32)
-k_consensus(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, const PairDesc* __restrict__ pairs,
+// ------------------------------------------------------------------------------ k_transpose
+// Per-read entry arrays (read-major, written sequentially by k_traceback) -> per-block
+// position-major pile-up matrix M[i][j] (i = seed position, j = pair index in the block, row
+// length rb_pad) so that k_consensus reads one coalesced 128-byte row segment per 32 reads and
+// position.  Entries outside a read's tagged range, of rejected pairs and of the padding are 0.
+// One warp per 32x32 tile through a padded shared-memory tile; reads and writes are coalesced.
+constexpr int TR_WARPS = 4;
+__global__ void __launch_bounds__(TR_WARPS * 32)
+k_transpose(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, uint32_t n_tiles,
             const PairRange* __restrict__ ranges, const PairAlloc* __restrict__ allocs,
-            const PairAln* __restrict__ aln, const uint32_t* __restrict__ pool,
-            const uint32_t* __restrict__ xam_arena, CnsRec* __restrict__ rec_arena,
-            uint16_t* __restrict__ cov_arena, int32_t* __restrict__ lvl_scratch,
-            uint32_t* __restrict__ acc_scratch, uint64_t acc_stride,
-            char* __restrict__ cns_arena, int32_t* __restrict__ eqv_arena, unsigned min_cov,
-            CnsOut* __restrict__ out) {
-    // per-warp link list of the current position
-    __shared__ uint32_t s_key[CNS_WARPS][LINK_CAP];    // (delta << 16) | (base << 13) | link
-    __shared__ uint16_t s_cnt[CNS_WARPS][LINK_CAP];
+            const PairAln* __restrict__ aln, const uint32_t* __restrict__ ent_arena,
+            uint32_t* __restrict__ m_arena) {
+    __shared__ uint32_t tile[TR_WARPS][32][33];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const uint32_t b = blockIdx.x * CNS_WARPS + wib;
-    if (b >= n_blocks) return;
-    const BlockDesc bd = blocks[b];
-    const uint32_t* seed = pool + bd.seed_woff;
-    const int t_len = bd.slen;
-    uint32_t* key = s_key[wib]; uint16_t* kcnt = s_cnt[wib];
-    CnsRec* recs = rec_arena + bd.rec_off;
-    uint16_t* cov = cov_arena + bd.cov_off;
-    // per-warp score/record tables of the previous and current position, indexed delta*5+base
-    const size_t gw = (size_t)blockIdx.x * CNS_WARPS + wib;
-    int32_t* lv_sc[2]  = { lvl_scratch + gw * 4 * LVL, lvl_scratch + gw * 4 * LVL + LVL };
-    int32_t* lv_rec[2] = { lvl_scratch + gw * 4 * LVL + 2 * LVL, lvl_scratch + gw * 4 * LVL + 3 * LVL };
-    // accepted reads of this block, in order
-    uint32_t* acc = acc_scratch + gw * acc_stride;
-    int R = 0;
-    for (uint32_t j0 = 0; j0 < bd.n_pairs; j0 += 32) {
-        uint32_t j = j0 + lane;
-        bool ok = j < bd.n_pairs && aln[bd.pair_begin + j].accepted;
-        unsigned bal = __ballot_sync(FULL, ok);
-        if (ok) acc[R + __popc(bal & lanemask_lt())] = bd.pair_begin + j;
-        R += __popc(bal);
-    }
-    __syncwarp();
-    CnsOut co; co.len = 0; co.err = 0;
-    char* cns = cns_arena + bd.cns_off;
-    int32_t* eqv = eqv_arena + bd.cns_off;
-    if (R == 0) { if (lane == 0) { cns[0] = 0; out[b] = co; } return; }     // falcon.c:651-656
-
-    // record 0 is reserved for column (0,0,'A'): the target of floored columns' best_p = (0,0,0)
-    if (lane == 0) { recs[0].pred = 0; recs[0].info = 0; recs[0].score2 = -2; }
-    uint32_t nrec = 1;
-    int g_best2 = -2, g_rec = -1, g_ck = 0, g_t = 0;
-    int cur = 0;
-    int err = 0;
-
-    for (int i = 0; i < t_len; i++) {
-        const int Si = base_at(seed, i);
-        const int Sp = i > 0 ? base_at(seed, i - 1) : 0;
-        int nlink = 0, coverage = 0, maxd = 0;
-        // ------------------------------------------------------------ vote
-        for (int c0 = 0; c0 < R; c0 += 32) {
-            const int ai = c0 + lane;
-            bool act = false; int y = 0; uint32_t pidx = 0; int ts = 0;
-            if (ai < R) {
-                pidx = acc[ai];
-                ts = ranges[pidx].s2;
-                y = i - ts;
-                act = y >= 0 && y < aln[pidx].t_cnt;
-            }
-            unsigned actb = __ballot_sync(FULL, act);
-            if (!actb) continue;
-            coverage += __popc(actb);
-            // lane state
-            int m = 0, x = 0, nins = 0, b0 = 0; uint32_t lk0 = 0;
-            const uint32_t* qr = pool; int qs = 0;
-            if (act) {
-                const uint32_t* xam = xam_arena + allocs[pidx].xam_off;
-                uint32_t c = xam[y], nx = xam[y + 1];
-                m = c & 1; x = (int)(c >> 1); nins = (int)(nx >> 1) - x - m;
-                b0 = m ? Si : 4;
-                qr = pool + pairs[pidx].read_woff; qs = ranges[pidx].s1;
-                if (y == 0) lk0 = 0x1fffu;                         // (p_t_pos = -1, 0, '.')
-                else {
-                    uint32_t pv = xam[y - 1];
-                    int pm = pv & 1, px = (int)(pv >> 1), pn = x - px - pm;
-                    int pb = pn > 0 ? base_at(qr, qs + x - 1) : (pm ? Sp : 4);
-                    lk0 = ((uint32_t)pn << 3) | (uint32_t)pb;
-                }
-            }
-            int lmax = __reduce_max_sync(FULL, act ? nins : 0);
-            maxd = max(maxd, lmax);
-            // levels 0..lmax of this chunk, merged in (level, lane) order.  Merging level by
-            // level is equivalent to read-by-read order: first appearance of a link inside one
-            // column is decided by the read index alone.
-            for (int lev = 0; lev <= lmax; lev++) {
-                bool has = act && nins >= lev;
-                uint32_t k = 0xffffffffu - lane;
-                if (has) {
-                    if (lev == 0) k = ((uint32_t)b0 << 13) | lk0;
-                    else {
-                        int bb = base_at(qr, qs + x + m + lev - 1);
-                        int pb = (lev == 1) ? b0 : base_at(qr, qs + x + m + lev - 2);
-                        k = ((uint32_t)lev << 16) | ((uint32_t)bb << 13) | ((uint32_t)(lev - 1) << 3) | (uint32_t)pb;
-                    }
-                }
-                unsigned peers = __match_any_sync(FULL, k);
-                bool leader = has && (__popc(peers & lanemask_lt()) == 0);
-                int pc = __popc(peers);
-                unsigned lead = __ballot_sync(FULL, leader);
-                while (lead) {
-                    int l = __ffs(lead) - 1; lead &= lead - 1;
-                    uint32_t kk = __shfl_sync(FULL, k, l); int cc = __shfl_sync(FULL, pc, l);
-                    int found = -1;
-                    for (int e0 = 0; e0 < nlink; e0 += 32) {
-                        unsigned hb = __ballot_sync(FULL, (e0 + lane < nlink) && key[e0 + lane] == kk);
-                        if (hb) { found = e0 + __ffs(hb) - 1; break; }
-                    }
-                    if (found >= 0) { if (lane == 0) kcnt[found] = (uint16_t)(kcnt[found] + cc); }
-                    else if (nlink < LINK_CAP) { if (lane == 0) { key[nlink] = kk; kcnt[nlink] = (uint16_t)cc; } nlink++; }
-                    else err = 1;
-                    __syncwarp();
-                }
-            }
-        }
-        if (lane == 0) cov[i] = (uint16_t)min(coverage, 65535);
-        if (coverage == 0) { cur ^= 1; continue; }    // no tags here: max_delta = 0, all columns dead
-        // ------------------------------------------------------------ DP over (j, kk)
-        int32_t* sc_p = lv_sc[cur ^ 1]; int32_t* rc_p = lv_rec[cur ^ 1];
-        int32_t* sc_c = lv_sc[cur];     int32_t* rc_c = lv_rec[cur];
-        for (int j = 0; j <= maxd; j++) {
-            for (int kk = 0; kk < 5; kk++) {
-                // scan the link list for column (j, kk); list order == first-appearance order
-                const uint32_t want = ((uint32_t)j << 3) | (uint32_t)kk;       // key >> 13
-                bool any = false;
-                int seen = 0;          // links of this column seen in earlier list windows
-                long long bkey = LLONG_MIN; int brec = -1, bsc2 = 0;
-                for (int e0 = 0; e0 < nlink; e0 += 32) {
-                    int e = e0 + lane;
-                    bool mine = e < nlink && (key[e] >> 13) == want;
-                    unsigned mb = __ballot_sync(FULL, mine);
-                    if (!mb) continue;
-                    any = true;
-                    long long v = LLONG_MIN; int prc = -1; int s2v = 0;
-                    if (mine) {
-                        uint32_t lk = key[e] & 0x1fffu;
-                        int cnt = kcnt[e];
-                        int s2 = 2 * cnt - coverage;                      // 2*(count - 0.5*cov)
-                        if (lk != 0x1fffu) {
-                            int pdl = lk >> 3, pbb = lk & 7;
-                            const int32_t* sc_src = (j == 0) ? sc_p : sc_c;
-                            const int32_t* rc_src = (j == 0) ? rc_p : rc_c;
-                            s2 += sc_src[pdl * 5 + pbb];
-                            prc = rc_src[pdl * 5 + pbb];
-                        }
-                        s2v = s2;
-                        // order: higher score first, then earlier list position
-                        v = (long long)s2 * (1ll << 20) + (long long)(0xfffff - (seen + __popc(mb & lanemask_lt())));
-                    }
-                    long long wm = v;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) { long long ov = __shfl_xor_sync(FULL, wm, o); wm = ov > wm ? ov : wm; }
-                    if (wm > bkey) {
-                        unsigned who = __ballot_sync(FULL, mine && v == wm);
-                        int wl = __ffs(who) - 1;
-                        bkey = wm; brec = __shfl_sync(FULL, prc, wl); bsc2 = __shfl_sync(FULL, s2v, wl);
-                    }
-                    seen += __popc(mb);
-                }
-                if (!any) { if (lane == 0) { sc_c[j * 5 + kk] = -2; rc_c[j * 5 + kk] = 0; } continue; }  // dead column: score -1
-                int best_ck = 0xfffff - (int)(bkey & 0xfffff);
-                int col_sc2, col_pred;
-                if (bsc2 > -2) { col_sc2 = bsc2; col_pred = brec; }      // recorded only if score > -1
-                else { col_sc2 = -2; col_pred = 0; best_ck = -1; }        // floored: best_p = (0,0,0)
-                // column record
-                uint32_t ridx;
-                if (i == 0 && j == 0 && kk == 0) ridx = 0; else { ridx = nrec; nrec++; }
-                if (ridx >= bd.rec_cap) { err = 2; ridx = bd.rec_cap - 1; }
-                if (lane == 0) {
-                    recs[ridx].pred = col_pred; recs[ridx].info = (i << 3) | kk; recs[ridx].score2 = col_sc2;
-                    sc_c[j * 5 + kk] = col_sc2; rc_c[j * 5 + kk] = (int32_t)ridx;
-                }
-                if (col_sc2 > g_best2) { g_best2 = col_sc2; g_rec = (int)ridx; g_ck = best_ck; g_t = i; }
-            }
-            __syncwarp();
-        }
-        cur ^= 1;
-        __syncwarp();
-    }
-    // ------------------------------------------------------------ backtrack (falcon.c:479-542)
-    if (g_rec < 0) err = 3;                       // reference: assert(g_best_score != -1)
-    __syncwarp();
-    int index = 0;
-    if (lane == 0 && err == 0) {
-        char bb = '$'; int ck = g_ck; int i = g_t; int rc = g_rec;
-        const unsigned lim = (unsigned)t_len * 2u;
-        for (;;) {
-            const bool hi = (unsigned)cov[i] > min_cov;
-            switch (ck) {
-                case 0: bb = hi ? 'A' : 'a'; break;
-                case 1: bb = hi ? 'C' : 'c'; break;
-                case 2: bb = hi ? 'G' : 'g'; break;
-                case 3: bb = hi ? 'T' : 't'; break;
-                case 4: bb = '-'; break;
-                default: break;
-            }
-            const CnsRec r = recs[rc];
-            if (r.pred == -1 || (unsigned)index >= lim) break;
-            const CnsRec pr = recs[r.pred];
-            i = pr.info >> 3; ck = pr.info & 7;
-            if (bb != '-') { cns[index] = bb; eqv[index] = r.score2 / 2 - pr.score2 / 2; index++; }
-            rc = r.pred;
+    const uint32_t T = blockIdx.x * TR_WARPS + wib;
+    if (T >= n_tiles) return;
+    uint32_t lo = 0, hi = n_blocks;                 // last block with tile_begin <= T
+    while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (blocks[mid].tile_begin <= T) lo = mid; else hi = mid; }
+    const BlockDesc bd = blocks[lo];
+    const uint32_t tl = T - bd.tile_begin;
+    const uint32_t jt = bd.rb_pad >> 5;             // tiles per row
+    const int i0 = (int)(tl / jt) * 32, j0 = (int)(tl % jt) * 32;
+    // lane r owns read j0 + r for the metadata
+    int my_ts = 0, my_cnt = 0; uint64_t my_off = 0;
+    {
+        const uint32_t j = (uint32_t)j0 + lane;
+        if (j < bd.n_pairs) {
+            const uint32_t p = bd.pair_begin + j;
+            const PairAln a = aln[p];
+            if (a.accepted) { my_ts = ranges[p].s2; my_cnt = a.t_cnt; my_off = allocs[p].xam_off; }
         }
     }
-    index = __shfl_sync(FULL, index, 0);
-    __syncwarp();
-    // reverse in place (falcon.c:533-540)
-    for (int a = lane; a < index / 2; a += 32) {
-        char tc = cns[a]; cns[a] = cns[index - 1 - a]; cns[index - 1 - a] = tc;
-        int te = eqv[a]; eqv[a] = eqv[index - 1 - a]; eqv[index - 1 - a] = te;
+    const int i = i0 + lane;
+#pragma unroll 4
+    for (int r = 0; r < 32; r++) {
+        const int ts = __shfl_sync(FULL, my_ts, r), cnt = __shfl_sync(FULL, my_cnt, r);
+        const uint64_t off = __shfl_sync(FULL, my_off, r);
+        const int y = i - ts;
+        uint32_t v = 0;
+        if (y >= 0 && y < cnt) v = ent_arena[off + y];
+        tile[wib][r][lane] = v;
     }
-    if (lane == 0) { cns[index] = 0; co.len = index; co.err = err; out[b] = co; }
+    __syncwarp();
+    uint32_t* M = m_arena + bd.m_off;
+#pragma unroll 4
+    for (int c = 0; c < 32; c++) {
+        const int ii = i0 + c;
+        if (ii < bd.slen) M[(size_t)ii * bd.rb_pad + j0 + lane] = tile[wib][lane][c];
+    }
 }
 
 }  // namespace fcx
+
+#include "fcx_consensus.cuh"

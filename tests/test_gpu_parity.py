@@ -73,6 +73,25 @@ def test_edge_blocks(engine, oracle):
         assert engine.generate_consensus(seqs, 0, 0.70) == oracle.generate_consensus(seqs, 0, 0.70)
 
 
+def test_low_complexity_match_list_overflow(engine, oracle):
+    """A shared 400-base homopolymer gives > 16384 k-mer hits for one pair: the range kernel must
+    leave its materialised-list fast path and still agree with the reference semantics."""
+    rng = np.random.default_rng(8)
+    g = synth.random_codes(6000, rng)
+    g[2500:2900] = 0
+    seed = synth.codes_to_bytes(g)
+    reads = [synth.codes_to_bytes(synth.add_errors(g, rng, 0.03, 0.02, 0.01)) for _ in range(5)]
+    seqs = [seed, seed] + reads
+    engine.upload_pool(seqs)
+    got = engine.consensus_blocks([list(range(len(seqs)))], 2, 0.70)[0]
+    info = engine.pair_info()
+    want, oinfo = oracle.generate_consensus(seqs, 2, 0.70, want_info=True)
+    assert max(i.n_match for i in info) > 16384
+    for g_, o_ in zip(info, oinfo[1:]):
+        assert (g_.n_match, g_.s1, g_.e1, g_.s2, g_.e2) == (o_.n_match, o_.s1, o_.e1, o_.s2, o_.e2)
+    assert got == want
+
+
 def test_rejects_non_acgt(engine):
     from falcon_b200.binding import EngineError
     with pytest.raises(EngineError):
