@@ -218,9 +218,8 @@ def main():
     buf, off, block_off, ids = flatten(S)
     n_pairs = int(S.n_pairs)
     eng = Engine(local_rank)
+    eng.set_option("pair_info", 0)
     L = lib()
-    L.fcx_timer_start.argtypes = [C.c_void_p]
-    L.fcx_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
 
     def barrier():
         torch.cuda.synchronize()

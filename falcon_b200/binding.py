@@ -109,6 +109,9 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
                                          C.POINTER(C.c_void_p)]
     lib.fcx_last_pair_info.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     lib.fcx_last_stats.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+    lib.fcx_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+    lib.fcx_timer_start.argtypes = [C.c_void_p]
+    lib.fcx_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     return lib
 
 
@@ -183,6 +186,9 @@ class Engine:
     def _check(self, rc: int, what: str):
         if rc != 0:
             raise EngineError("%s: %s" % (what, self._lib.fcx_last_error(self._h).decode()))
+
+    def set_option(self, name: str, value: float):
+        self._check(self._lib.fcx_set_option(self._h, name.encode(), float(value)), "fcx_set_option")
 
     # -- pool ---------------------------------------------------------------------------
     def upload_pool_raw(self, bases_ptr: int, offsets: np.ndarray):

@@ -176,50 +176,52 @@ k_consensus(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, const PairD
         long long tk0 = 0;
         if (PROF) tk0 = clock64();
         // =============================================================== fast vote
+        // Straight-line over the row chunks (no per-chunk collectives on the critical path): every
+        // lane decodes its entry, the dominant link "match after match" (col 0, pd 0, pb = seed
+        // base) is counted with one ballot per chunk, everything else goes through shared-memory
+        // atomics; coverage / max_delta / deep are reduced once at the end.
         if (rows_in_regs) {
+            const int idx_maj = 1 + Sp;
+            int cov_lane = 0, nins_lane = 0, maj_cnt = 0, maj_first = NOFIRST; bool deep_lane = false;
 #pragma unroll
             for (int c = 0; c < NCHR; c++) {
                 if (c * 32 >= RB) continue;
-                const uint32_t ec = ecv[c];
+                const uint32_t ec = ecv[c], ep = epv[c];
                 const bool act = (ec & ENT_VALID) != 0;
-                const unsigned actb = __ballot_sync(FULL, act);
-                if (!actb) continue;
-                coverage += __popc(actb);
-                if (deep) continue;
-                const uint32_t ep = epv[c];
                 const int ai = c * 32 + lane;
                 const int m = (ec & ENT_MATCH) ? 1 : 0;
                 const int nins = act ? ent_nins(ec) : 0;
                 const int b0 = m ? Si : 4;
-                int idx0 = 0; bool dp_lane = false;
-                if (act) {
-                    int l0 = 0;
-                    if (ep & ENT_VALID) {
-                        const int pn = ent_nins(ep);
-                        if (pn > FJ) dp_lane = true;
-                        else {
-                            const int pb = pn > 0 ? ent_ins(ep, pn - 1) : ((ep & ENT_MATCH) ? Sp : 4);
-                            l0 = 1 + pn * 5 + pb;
-                        }
-                    }
-                    if (nins > FJ) dp_lane = true;
-                    idx0 = (m ? 0 : T0W) + l0;
+                int l0 = 0; bool dpl = nins > FJ;
+                if (ep & ENT_VALID) {
+                    const int pn = ent_nins(ep);
+                    dpl = dpl || pn > FJ;
+                    const int pb = pn > 0 ? ent_ins(ep, (pn - 1) & 7) : ((ep & ENT_MATCH) ? Sp : 4);
+                    l0 = 1 + (pn & 3) * 5 + pb;
                 }
-                if (__ballot_sync(FULL, dp_lane)) { deep = true; continue; }
-                if (act) { atomicAdd(&sm.cnt[idx0], 1); atomicMin(&sm.first[idx0], ai); }   // delta-0 votes
-                const int lmax = __reduce_max_sync(FULL, nins);
-                maxd = max(maxd, lmax);
-                for (int lev = 1; lev <= lmax; lev++) {
-                    const bool has = nins >= lev;
-                    int idx = 0;
-                    if (has) {
+                const int idx0 = (m ? 0 : T0W) + l0;
+                cov_lane += act ? 1 : 0;
+                nins_lane = max(nins_lane, nins);
+                deep_lane = deep_lane || (act && dpl);
+                const bool vote = act && !dpl;
+                const unsigned majb = __ballot_sync(FULL, vote && idx0 == idx_maj);
+                maj_cnt += __popc(majb);
+                if (majb && maj_first == NOFIRST) maj_first = c * 32 + __ffs(majb) - 1;
+                if (vote && idx0 != idx_maj) { atomicAdd(&sm.cnt[idx0], 1); atomicMin(&sm.first[idx0], ai); }
+#pragma unroll
+                for (int lev = 1; lev <= FJ; lev++) {
+                    if (vote && nins >= lev) {
                         const int bb = ent_ins(ec, lev - 1);
                         const int pb = (lev == 1) ? b0 : ent_ins(ec, lev - 2);
-                        idx = DENSE0 + (lev - 1) * 20 + bb * 5 + pb;
+                        const int idx = DENSE0 + (lev - 1) * 20 + bb * 5 + pb;
+                        atomicAdd(&sm.cnt[idx], 1); atomicMin(&sm.first[idx], ai);
                     }
-                    if (has) { atomicAdd(&sm.cnt[idx], 1); atomicMin(&sm.first[idx], ai); }
                 }
             }
+            if (lane == 0 && maj_cnt) { sm.cnt[idx_maj] = maj_cnt; sm.first[idx_maj] = maj_first; }
+            deep = __ballot_sync(FULL, deep_lane) != 0;
+            coverage = __reduce_add_sync(FULL, cov_lane);
+            maxd = __reduce_max_sync(FULL, nins_lane);
             __syncwarp();
         }
         if (PROF) { const long long tk1 = clock64(); cyc_vote += tk1 - tk0; tk0 = tk1; }
@@ -279,14 +281,15 @@ k_consensus(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, const PairD
                     if (valid) { s2 = 2 * cntv - coverage + tc.s_sc[(j - 1) * 5 + pb]; prj = tc.s_rc[(j - 1) * 5 + pb]; }
                     const unsigned vb = __ballot_sync(FULL, valid);
                     if (!vb) continue;
-                    int mx = s2;                                   // max over the 8-lane group
-                    mx = max(mx, __shfl_xor_sync(FULL, mx, 1)); mx = max(mx, __shfl_xor_sync(FULL, mx, 2));
-                    mx = max(mx, __shfl_xor_sync(FULL, mx, 4));
-                    int fm = (valid && s2 == mx) ? fst : NOFIRST;   // earliest voter among the maxima
-                    fm = min(fm, __shfl_xor_sync(FULL, fm, 1)); fm = min(fm, __shfl_xor_sync(FULL, fm, 2));
-                    fm = min(fm, __shfl_xor_sync(FULL, fm, 4));
-                    const unsigned wb = __ballot_sync(FULL, valid && s2 == mx && fst == fm);
-                    const unsigned eb = __ballot_sync(FULL, valid && fst < fm);       // links before the winner
+                    // one keyed butterfly over the 8-lane group: highest score, then earliest voter
+                    long long kv = valid ? (long long)s2 * 4294967296ll + (long long)(0x7fffffff - fst) : LLONG_MIN;
+                    long long km = kv;
+#pragma unroll
+                    for (int o = 1; o < 8; o <<= 1) { const long long ov = __shfl_xor_sync(FULL, km, o); km = ov > km ? ov : km; }
+                    const int mx = valid || km != LLONG_MIN ? (int)(km >> 32) : INT_MIN;
+                    const int fm = 0x7fffffff - (int)(km & 0x7fffffffll);
+                    const unsigned wb = __ballot_sync(FULL, valid && kv == km);
+                    const unsigned eb = __ballot_sync(FULL, valid && fst < fm && km != LLONG_MIN);       // links before the winner
 #pragma unroll
                     for (int g = 0; g < 4; g++) {
                         const unsigned gm = 0xffu << (8 * g);

@@ -1,16 +1,23 @@
 // fcx_engine.cu -- host side of libfalcon_b200.so: device memory, wave planning, launches and
 // the batched C ABI declared in include/falcon_b200.h.  There is NO CPU path for the arithmetic:
-// every stage runs in the CUDA kernels of fcx_kernels.cuh and any CUDA failure is reported (fcx_*)
-// or fatal (legacy symbols), never papered over.
+// every stage runs in the CUDA kernels of fcx_kernels.cuh / fcx_consensus.cuh and any CUDA failure
+// is reported (fcx_*) or fatal (legacy symbols), never papered over.
+//
+// Execution model: a call is cut into WAVES of seed blocks; waves are independent and run on LANES
+// (one host thread + CUDA stream + buffer set each).  Several lanes in flight let the latency-bound
+// kernels of one wave (k_consensus: one warp per block, a serial chain over the seed) overlap the
+// issue-bound kernels of another (k_dp), which is where the throughput comes from.
 #include "fcx_kernels.cuh"
 #include "../../include/falcon_b200.h"
 
 #include <algorithm>
+#include <atomic>
 #include <climits>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace fcx;
@@ -44,26 +51,53 @@ struct HostBuf {              // grow-only pinned host buffer
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+struct Lane {                 // one in-flight wave: stream, events, buffers, statistics
+    cudaStream_t stream = nullptr;
+    cudaStream_t stream_hi = nullptr;   // high priority: the latency-bound consensus kernel
+    cudaEvent_t ev[8] = {nullptr};
+    DevBuf d_blocks, d_pairs, d_ranges, d_allocs, d_aln, d_ktab, d_kpos, d_trace, d_path, d_xam, d_ent, d_M,
+           d_rlist, d_recs, d_lvl, d_meta, d_cns, d_eqv, d_cnsout;
+    HostBuf h_ranges, h_aln, h_cns, h_cnsout, h_eqv;
+    std::string err;
+    double times[FCX_T_COUNT] = {0};
+    uint64_t counters[FCX_C_COUNT] = {0};
+    double prof[8] = {0};
+    void release() {
+        DevBuf* bufs[] = {&d_blocks, &d_pairs, &d_ranges, &d_allocs, &d_aln, &d_ktab, &d_kpos, &d_trace, &d_path,
+                          &d_xam, &d_ent, &d_M, &d_rlist, &d_recs, &d_lvl, &d_meta, &d_cns, &d_eqv, &d_cnsout};
+        for (auto* b : bufs) b->release();
+        HostBuf* hb[] = {&h_ranges, &h_aln, &h_cns, &h_cnsout, &h_eqv};
+        for (auto* b : hb) b->release();
+        for (auto& e : ev) if (e) { cudaEventDestroy(e); e = nullptr; }
+        if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
+        if (stream_hi) { cudaStreamDestroy(stream_hi); stream_hi = nullptr; }
+    }
+};
+
+struct WaveResult {
+    std::vector<char> bases;
+    std::vector<uint64_t> lens;
+    std::vector<fcx_pair_info> info;
+    std::vector<int32_t> eqv;
+};
+
 }  // namespace
 
 struct fcx_ctx {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;     // pool uploads, single-pair align, stopwatch
     std::string err;
     // pool
     uint32_t n_reads = 0;
     std::vector<uint64_t> h_woff;      // n_reads + 1
     std::vector<int32_t> h_len;
     DevBuf d_pool, d_ascii, d_aoff, d_woff, d_len, d_dirty;
-    // wave buffers
-    DevBuf d_blocks, d_pairs, d_ranges, d_allocs, d_aln, d_ktab, d_kpos, d_trace, d_path, d_xam, d_ent, d_M,
-           d_recs, d_cov, d_lvl, d_acc, d_cns, d_eqv, d_cnsout;
-    DevBuf d_rlist;
+    // single-pair align scratch
+    DevBuf d_trace1, d_path1, d_aln1, d_str1;
+    std::vector<Lane> lanes;
     int sm_count = 148;
     bool profile = false;
-    double prof[8] = {0};
-    HostBuf h_ranges, h_aln, h_cns, h_cnsout, h_stage, h_eqv;
-    // results
+    // results of the last call
     std::vector<char> out_bases;
     std::vector<uint64_t> out_off;
     std::vector<fcx_pair_info> pair_info;
@@ -72,28 +106,32 @@ struct fcx_ctx {
     bool keep_pair_info = true;
     double times[FCX_T_COUNT] = {0};
     uint64_t counters[FCX_C_COUNT] = {0};
-    cudaEvent_t ev[8] = {nullptr};
+    double prof[8] = {0};
     cudaEvent_t tev[2] = {nullptr, nullptr};
-    size_t arena_budget = (size_t)110 << 30;
-    uint32_t max_wave_blocks = 4096;
+    size_t arena_budget = (size_t)120 << 30;
+    uint32_t max_wave_blocks = 2368;     // 148 SMs x 16 resident consensus warps
     uint32_t max_wave_pairs = 1u << 19;
+    uint32_t min_wave_blocks = 384;
+    int n_lanes = 2;
 };
 
 static thread_local std::string g_create_err;
 
-#define CK(call)                                                                          \
+#define CKE(errstr, call)                                                                 \
     do {                                                                                  \
         cudaError_t e_ = (call);                                                          \
         if (e_ != cudaSuccess) {                                                          \
             char buf_[512];                                                               \
             snprintf(buf_, sizeof buf_, "%s failed: %s (%s:%d)", #call,                   \
                      cudaGetErrorString(e_), __FILE__, __LINE__);                         \
-            ctx->err = buf_;                                                              \
+            (errstr) = buf_;                                                              \
             return 1;                                                                     \
         }                                                                                 \
     } while (0)
+#define CK(call) CKE(ctx->err, call)
+#define CKL(call) CKE(L.err, call)
 
-extern "C" const char* fcx_version(void) { return "falcon_b200 0.1 sm_100a"; }
+extern "C" const char* fcx_version(void) { return "falcon_b200 0.2 sm_100a"; }
 
 extern "C" const char* fcx_last_error(const fcx_ctx* ctx) {
     return ctx ? ctx->err.c_str() : g_create_err.c_str();
@@ -115,16 +153,25 @@ extern "C" int fcx_create(int device, fcx_ctx** out) {
         g_create_err = "cudaSetDevice/cudaStreamCreate failed";
         delete ctx; return 1;
     }
-    for (auto& ev : ctx->ev) cudaEventCreate(&ev);
     for (auto& ev : ctx->tev) cudaEventCreate(&ev);
-    if (const char* s = getenv("FCX_ARENA_GB")) ctx->arena_budget = (size_t)atof(s) * ((size_t)1 << 30);
-    if (const char* s = getenv("FCX_WAVE_BLOCKS")) ctx->max_wave_blocks = (uint32_t)atoi(s);
+    if (const char* s = getenv("FCX_ARENA_GB")) ctx->arena_budget = (size_t)(atof(s) * (double)((size_t)1 << 30));
+    if (const char* s = getenv("FCX_WAVE_BLOCKS")) { ctx->max_wave_blocks = (uint32_t)atoi(s); ctx->min_wave_blocks = std::min(ctx->min_wave_blocks, ctx->max_wave_blocks); }
     if (const char* s = getenv("FCX_WAVE_PAIRS")) ctx->max_wave_pairs = (uint32_t)atoi(s);
+    if (const char* s = getenv("FCX_LANES")) ctx->n_lanes = std::max(1, atoi(s));
     if (const char* s = getenv("FCX_PROFILE")) ctx->profile = atoi(s) != 0;
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
-    // dynamic shared memory opt-in for k_range
     cudaFuncSetAttribute(k_range, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          RANGE_WARPS * RANGE_BINS * (int)sizeof(int));
+    ctx->lanes.resize(ctx->n_lanes);
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    for (auto& L : ctx->lanes) {
+        if (cudaStreamCreateWithPriority(&L.stream, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
+            cudaStreamCreateWithPriority(&L.stream_hi, cudaStreamNonBlocking, prio_hi) != cudaSuccess) {
+            g_create_err = "cudaStreamCreate (lane) failed"; fcx_destroy(ctx); return 1;
+        }
+        for (auto& ev : L.ev) cudaEventCreate(&ev);
+    }
     *out = ctx;
     return 0;
 }
@@ -132,17 +179,13 @@ extern "C" int fcx_create(int device, fcx_ctx** out) {
 extern "C" void fcx_destroy(fcx_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    cudaDeviceSynchronize();
     DevBuf* bufs[] = {&ctx->d_pool, &ctx->d_ascii, &ctx->d_aoff, &ctx->d_woff, &ctx->d_len, &ctx->d_dirty,
-                      &ctx->d_blocks, &ctx->d_pairs, &ctx->d_ranges, &ctx->d_allocs, &ctx->d_aln,
-                      &ctx->d_ktab, &ctx->d_kpos, &ctx->d_trace, &ctx->d_path, &ctx->d_xam, &ctx->d_ent, &ctx->d_M, &ctx->d_rlist, &ctx->d_recs,
-                      &ctx->d_cov, &ctx->d_lvl, &ctx->d_acc, &ctx->d_cns, &ctx->d_eqv, &ctx->d_cnsout};
+                      &ctx->d_trace1, &ctx->d_path1, &ctx->d_aln1, &ctx->d_str1};
     for (auto* b : bufs) b->release();
-    HostBuf* hb[] = {&ctx->h_ranges, &ctx->h_aln, &ctx->h_cns, &ctx->h_cnsout, &ctx->h_stage, &ctx->h_eqv};
-    for (auto* b : hb) b->release();
-    for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& L : ctx->lanes) L.release();
     for (auto& ev : ctx->tev) if (ev) cudaEventDestroy(ev);
-    cudaStreamDestroy(ctx->stream);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 
@@ -152,6 +195,18 @@ extern "C" void* fcx_host_alloc(size_t bytes) {
     return p;
 }
 extern "C" void fcx_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+extern "C" int fcx_set_option(fcx_ctx* ctx, const char* name, double value) {
+    std::string n(name);
+    if (n == "pair_info") ctx->keep_pair_info = value != 0;
+    else if (n == "eqv") ctx->want_eqv = value != 0;
+    else if (n == "profile") ctx->profile = value != 0;
+    else if (n == "arena_gb") ctx->arena_budget = (size_t)(value * (double)((size_t)1 << 30));
+    else if (n == "max_wave_blocks") ctx->max_wave_blocks = (uint32_t)value;
+    else if (n == "min_wave_blocks") ctx->min_wave_blocks = (uint32_t)value;
+    else { ctx->err = "unknown option: " + n; return 1; }
+    return 0;
+}
 
 // ---------------------------------------------------------------------------------- pool
 extern "C" int fcx_pool_upload(fcx_ctx* ctx, const char* bases, const uint64_t* offsets, uint32_t n_reads) {
@@ -202,15 +257,13 @@ extern "C" int fcx_pool_upload(fcx_ctx* ctx, const char* bases, const uint64_t* 
 // ---------------------------------------------------------------------------------- waves
 namespace {
 
-struct WavePlan { uint32_t b0, b1; };
-
 inline uint64_t max_d_of(int q_len, int t_len) { return (uint64_t)(int)(0.3 * (q_len + t_len)); }
 
-int run_wave(fcx_ctx* ctx, uint32_t b0, uint32_t b1, const uint32_t* block_off, const uint32_t* read_ids,
-             unsigned min_cov, double min_idt, uint64_t pair_base) {
+int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* block_off, const uint32_t* read_ids,
+             unsigned min_cov, double min_idt, WaveResult& res) {
     const uint32_t nb = b1 - b0;
     std::vector<BlockDesc> hb(nb);
-    uint64_t npairs64 = 0, kpos_total = 0, rec_total = 0, cns_total = 0, cov_total = 0, m_total = 0, tiles = 0;
+    uint64_t npairs64 = 0, kpos_total = 0, rec_total = 0, cns_total = 0, m_total = 0, tiles = 0;
     uint32_t max_np = 1;
     for (uint32_t b = 0; b < nb; b++) {
         uint32_t lo = block_off[b0 + b], hi = block_off[b0 + b + 1];
@@ -224,7 +277,7 @@ int run_wave(fcx_ctx* ctx, uint32_t b0, uint32_t b1, const uint32_t* block_off, 
         d.rec_cap = (uint32_t)std::max<int64_t>(64, (int64_t)d.slen * 8 + 64);
         d.rec_off = rec_total; rec_total += d.rec_cap;
         d.cns_off = cns_total; cns_total += (uint64_t)d.slen * 2 + 8;
-        d.cov_off = cov_total; cov_total += (uint64_t)d.slen + 8;
+        d.cov_off = 0;
         d.rb_pad = (d.n_pairs + 31u) & ~31u;
         d.m_off = m_total; m_total += (uint64_t)d.rb_pad * (uint64_t)std::max(d.slen, 1);
         d.tile_begin = (uint32_t)tiles; tiles += (uint64_t)((d.slen + 31) / 32) * (d.rb_pad / 32);
@@ -241,54 +294,55 @@ int run_wave(fcx_ctx* ctx, uint32_t b0, uint32_t b1, const uint32_t* block_off, 
             pd.read_woff = ctx->h_woff[rid]; pd.block = b; pd.rlen = ctx->h_len[rid];
         }
     }
-    cudaStream_t st = ctx->stream;
-    CK(ctx->d_blocks.reserve(nb * sizeof(BlockDesc)));
-    CK(ctx->d_pairs.reserve((size_t)std::max(np, 1u) * sizeof(PairDesc)));
-    CK(ctx->d_ranges.reserve((size_t)std::max(np, 1u) * sizeof(PairRange)));
-    CK(ctx->d_allocs.reserve((size_t)std::max(np, 1u) * sizeof(PairAlloc)));
-    CK(ctx->d_aln.reserve((size_t)std::max(np, 1u) * sizeof(PairAln)));
-    CK(ctx->d_ktab.reserve((size_t)nb * KTAB * 4));
-    CK(ctx->d_kpos.reserve(kpos_total * 4 + 16));
-    CK(ctx->d_recs.reserve(rec_total * sizeof(CnsRec)));
-    CK(ctx->d_cns.reserve(cns_total));
-    CK(ctx->d_eqv.reserve(cns_total * 4));
-    CK(ctx->d_cnsout.reserve(nb * sizeof(CnsOut)));
+    cudaStream_t st = L.stream;
+    const size_t np1 = std::max(np, 1u);
+    CKL(L.d_blocks.reserve(nb * sizeof(BlockDesc)));
+    CKL(L.d_pairs.reserve(np1 * sizeof(PairDesc)));
+    CKL(L.d_ranges.reserve(np1 * sizeof(PairRange)));
+    CKL(L.d_allocs.reserve(np1 * sizeof(PairAlloc)));
+    CKL(L.d_aln.reserve(np1 * sizeof(PairAln)));
+    CKL(L.d_ktab.reserve((size_t)nb * KTAB * 4));
+    CKL(L.d_kpos.reserve(kpos_total * 4 + 16));
+    CKL(L.d_recs.reserve(rec_total * sizeof(CnsRec)));
+    CKL(L.d_cns.reserve(cns_total));
+    CKL(L.d_eqv.reserve(cns_total * 4));
+    CKL(L.d_cnsout.reserve(nb * sizeof(CnsOut)));
     const uint32_t cns_grid = (nb + CNS_WARPS - 1) / CNS_WARPS;
-    CK(ctx->d_lvl.reserve((size_t)cns_grid * CNS_WARPS * 4 * LVL * 4));
-    CK(ctx->d_acc.reserve((size_t)cns_grid * CNS_WARPS * max_np * sizeof(ReadMeta)));
-    CK(ctx->h_ranges.reserve((size_t)std::max(np, 1u) * sizeof(PairRange)));
-    CK(ctx->h_aln.reserve((size_t)std::max(np, 1u) * sizeof(PairAln)));
-    CK(ctx->h_cns.reserve(cns_total));
-    CK(ctx->h_cnsout.reserve(nb * sizeof(CnsOut)));
+    CKL(L.d_lvl.reserve((size_t)cns_grid * CNS_WARPS * 4 * LVL * 4));
+    CKL(L.d_meta.reserve((size_t)cns_grid * CNS_WARPS * max_np * sizeof(ReadMeta)));
+    CKL(L.h_ranges.reserve(np1 * sizeof(PairRange)));
+    CKL(L.h_aln.reserve(np1 * sizeof(PairAln)));
+    CKL(L.h_cns.reserve(cns_total));
+    CKL(L.h_cnsout.reserve(nb * sizeof(CnsOut)));
 
-    CK(cudaMemcpyAsync(ctx->d_blocks.p, hb.data(), nb * sizeof(BlockDesc), cudaMemcpyHostToDevice, st));
-    if (np) CK(cudaMemcpyAsync(ctx->d_pairs.p, hp.data(), (size_t)np * sizeof(PairDesc), cudaMemcpyHostToDevice, st));
+    CKL(cudaMemcpyAsync(L.d_blocks.p, hb.data(), nb * sizeof(BlockDesc), cudaMemcpyHostToDevice, st));
+    if (np) CKL(cudaMemcpyAsync(L.d_pairs.p, hp.data(), (size_t)np * sizeof(PairDesc), cudaMemcpyHostToDevice, st));
     const uint32_t* pool = ctx->d_pool.as<uint32_t>();
 
     // ---- index
-    CK(cudaEventRecord(ctx->ev[0], st));
-    CK(cudaMemsetAsync(ctx->d_ktab.p, 0, (size_t)nb * KTAB * 4, st));
-    k_index<<<nb, 256, 0, st>>>(ctx->d_blocks.as<BlockDesc>(), pool, ctx->d_ktab.as<uint32_t>(), ctx->d_kpos.as<uint32_t>());
-    CK(cudaGetLastError());
-    CK(cudaEventRecord(ctx->ev[1], st));
-    ctx->counters[FCX_C_KERNEL_LAUNCHES] += 1;
+    CKL(cudaEventRecord(L.ev[0], st));
+    CKL(cudaMemsetAsync(L.d_ktab.p, 0, (size_t)nb * KTAB * 4, st));
+    k_index<<<nb, 256, 0, st>>>(L.d_blocks.as<BlockDesc>(), pool, L.d_ktab.as<uint32_t>(), L.d_kpos.as<uint32_t>());
+    CKL(cudaGetLastError());
+    CKL(cudaEventRecord(L.ev[1], st));
+    L.counters[FCX_C_KERNEL_LAUNCHES] += 1;
     // ---- range
     if (np) {
         const unsigned rgrid = std::min<unsigned>((np + RANGE_WARPS - 1) / RANGE_WARPS, (unsigned)ctx->sm_count * 3u);
-        CK(ctx->d_rlist.reserve((size_t)rgrid * RANGE_WARPS * RANGE_LIST_CAP * sizeof(int2)));
+        CKL(L.d_rlist.reserve((size_t)rgrid * RANGE_WARPS * RANGE_LIST_CAP * sizeof(int2)));
         k_range<<<rgrid, RANGE_WARPS * 32, RANGE_WARPS * RANGE_BINS * sizeof(int), st>>>(
-            ctx->d_blocks.as<BlockDesc>(), ctx->d_pairs.as<PairDesc>(), np, pool, ctx->d_ktab.as<uint32_t>(),
-            ctx->d_kpos.as<uint32_t>(), ctx->d_rlist.as<int2>(), ctx->d_ranges.as<PairRange>());
-        CK(cudaGetLastError());
-        ctx->counters[FCX_C_KERNEL_LAUNCHES] += 1;
-        CK(cudaMemcpyAsync(ctx->h_ranges.p, ctx->d_ranges.p, (size_t)np * sizeof(PairRange), cudaMemcpyDeviceToHost, st));
+            L.d_blocks.as<BlockDesc>(), L.d_pairs.as<PairDesc>(), np, pool, L.d_ktab.as<uint32_t>(),
+            L.d_kpos.as<uint32_t>(), L.d_rlist.as<int2>(), L.d_ranges.as<PairRange>());
+        CKL(cudaGetLastError());
+        L.counters[FCX_C_KERNEL_LAUNCHES] += 1;
+        CKL(cudaMemcpyAsync(L.h_ranges.p, L.d_ranges.p, (size_t)np * sizeof(PairRange), cudaMemcpyDeviceToHost, st));
     }
-    CK(cudaEventRecord(ctx->ev[2], st));
-    CK(cudaStreamSynchronize(st));
+    CKL(cudaEventRecord(L.ev[2], st));
+    CKL(cudaStreamSynchronize(st));
     // ---- exact per-pair allocations
     std::vector<PairAlloc> ha(np);
     uint64_t trace_recs = 0, xam_n = 0, path_w = 0, dp_pairs = 0, span_bases = 0;
-    const PairRange* hr = ctx->h_ranges.as<PairRange>();
+    const PairRange* hr = L.h_ranges.as<PairRange>();
     for (uint32_t p = 0; p < np; p++) {
         ha[p].trace_off = trace_recs; ha[p].xam_off = xam_n; ha[p].path_off = path_w;
         if (hr[p].pass) {
@@ -298,83 +352,90 @@ int run_wave(fcx_ctx* ctx, uint32_t b0, uint32_t b1, const uint32_t* block_off, 
             dp_pairs++; span_bases += (uint64_t)ql + tl;
         }
     }
-    CK(ctx->d_trace.reserve(trace_recs * TRACE_REC_WORDS * 4 + 64));
-    CK(ctx->d_xam.reserve(xam_n * 4 + 64));
-    CK(ctx->d_ent.reserve(xam_n * 4 + 64));
-    CK(ctx->d_M.reserve(m_total * 4 + 64));
-    CK(ctx->d_path.reserve(path_w * 4 + 64));
-    if (np) CK(cudaMemcpyAsync(ctx->d_allocs.p, ha.data(), (size_t)np * sizeof(PairAlloc), cudaMemcpyHostToDevice, st));
+    CKL(L.d_trace.reserve(trace_recs * TRACE_REC_WORDS * 4 + 64));
+    CKL(L.d_xam.reserve(xam_n * 4 + 64));
+    CKL(L.d_ent.reserve(xam_n * 4 + 64));
+    CKL(L.d_path.reserve(path_w * 4 + 64));
+    CKL(L.d_M.reserve(m_total * 4 + 64));
+    if (np) CKL(cudaMemcpyAsync(L.d_allocs.p, ha.data(), (size_t)np * sizeof(PairAlloc), cudaMemcpyHostToDevice, st));
     // ---- DP
-    CK(cudaEventRecord(ctx->ev[3], st));
+    CKL(cudaEventRecord(L.ev[3], st));
     if (np) {
         k_dp<<<(np + DP_WARPS - 1) / DP_WARPS, DP_WARPS * 32, 0, st>>>(
-            ctx->d_blocks.as<BlockDesc>(), ctx->d_pairs.as<PairDesc>(), ctx->d_ranges.as<PairRange>(),
-            ctx->d_allocs.as<PairAlloc>(), np, pool, ctx->d_trace.as<uint32_t>(), 1.0 - min_idt, ctx->d_aln.as<PairAln>());
-        CK(cudaGetLastError());
-        ctx->counters[FCX_C_KERNEL_LAUNCHES] += 1;
+            L.d_blocks.as<BlockDesc>(), L.d_pairs.as<PairDesc>(), L.d_ranges.as<PairRange>(),
+            L.d_allocs.as<PairAlloc>(), np, pool, L.d_trace.as<uint32_t>(), 1.0 - min_idt, L.d_aln.as<PairAln>());
+        CKL(cudaGetLastError());
+        L.counters[FCX_C_KERNEL_LAUNCHES] += 1;
     }
-    CK(cudaEventRecord(ctx->ev[4], st));
-    // ---- traceback
+    CKL(cudaEventRecord(L.ev[4], st));
+    // ---- traceback + transpose
     if (np) {
         k_traceback<<<(np + 127) / 128, 128, 0, st>>>(
-            ctx->d_blocks.as<BlockDesc>(), ctx->d_pairs.as<PairDesc>(), ctx->d_ranges.as<PairRange>(),
-            ctx->d_allocs.as<PairAlloc>(), np, pool, ctx->d_trace.as<uint32_t>(), ctx->d_path.as<uint32_t>(),
-            ctx->d_xam.as<uint32_t>(), ctx->d_ent.as<uint32_t>(), ctx->d_aln.as<PairAln>());
-        CK(cudaGetLastError());
-        ctx->counters[FCX_C_KERNEL_LAUNCHES] += 1;
+            L.d_blocks.as<BlockDesc>(), L.d_pairs.as<PairDesc>(), L.d_ranges.as<PairRange>(),
+            L.d_allocs.as<PairAlloc>(), np, pool, L.d_trace.as<uint32_t>(), L.d_path.as<uint32_t>(),
+            L.d_xam.as<uint32_t>(), L.d_ent.as<uint32_t>(), L.d_aln.as<PairAln>());
+        CKL(cudaGetLastError());
+        L.counters[FCX_C_KERNEL_LAUNCHES] += 1;
     }
     if (tiles) {
         k_transpose<<<(unsigned)((tiles + TR_WARPS - 1) / TR_WARPS), TR_WARPS * 32, 0, st>>>(
-            ctx->d_blocks.as<BlockDesc>(), nb, (uint32_t)tiles, ctx->d_ranges.as<PairRange>(),
-            ctx->d_allocs.as<PairAlloc>(), ctx->d_aln.as<PairAln>(), ctx->d_ent.as<uint32_t>(), ctx->d_M.as<uint32_t>());
-        CK(cudaGetLastError());
-        ctx->counters[FCX_C_KERNEL_LAUNCHES] += 1;
+            L.d_blocks.as<BlockDesc>(), nb, (uint32_t)tiles, L.d_ranges.as<PairRange>(),
+            L.d_allocs.as<PairAlloc>(), L.d_aln.as<PairAln>(), L.d_ent.as<uint32_t>(), L.d_M.as<uint32_t>());
+        CKL(cudaGetLastError());
+        L.counters[FCX_C_KERNEL_LAUNCHES] += 1;
     }
-    CK(cudaEventRecord(ctx->ev[5], st));
-    // ---- consensus
+    CKL(cudaEventRecord(L.ev[5], st));
+    // ---- consensus: on the lane's high-priority stream so that its few, long-running CTAs are
+    // placed ahead of the next wave's bulk kernels and overlap them
+    cudaStream_t sh = L.stream_hi;
+    CKL(cudaStreamWaitEvent(sh, L.ev[5], 0));
     {
         auto kfn = ctx->profile ? k_consensus<true> : k_consensus<false>;
-        kfn<<<cns_grid, CNS_WARPS * 32, 0, st>>>(
-            ctx->d_blocks.as<BlockDesc>(), nb, ctx->d_pairs.as<PairDesc>(), ctx->d_ranges.as<PairRange>(),
-            ctx->d_allocs.as<PairAlloc>(), ctx->d_aln.as<PairAln>(), pool, ctx->d_xam.as<uint32_t>(),
-            ctx->d_M.as<uint32_t>(), ctx->d_recs.as<CnsRec>(), ctx->d_lvl.as<int32_t>(),
-            ctx->d_acc.as<ReadMeta>(), (uint64_t)max_np, ctx->d_cns.as<char>(), ctx->d_eqv.as<int32_t>(), min_cov,
-            ctx->d_cnsout.as<CnsOut>());
+        kfn<<<cns_grid, CNS_WARPS * 32, 0, sh>>>(
+            L.d_blocks.as<BlockDesc>(), nb, L.d_pairs.as<PairDesc>(), L.d_ranges.as<PairRange>(),
+            L.d_allocs.as<PairAlloc>(), L.d_aln.as<PairAln>(), pool, L.d_xam.as<uint32_t>(),
+            L.d_M.as<uint32_t>(), L.d_recs.as<CnsRec>(), L.d_lvl.as<int32_t>(),
+            L.d_meta.as<ReadMeta>(), (uint64_t)max_np, L.d_cns.as<char>(), L.d_eqv.as<int32_t>(), min_cov,
+            L.d_cnsout.as<CnsOut>());
     }
-    CK(cudaGetLastError());
-    ctx->counters[FCX_C_KERNEL_LAUNCHES] += 1;
-    CK(cudaEventRecord(ctx->ev[6], st));
-    CK(cudaMemcpyAsync(ctx->h_cnsout.p, ctx->d_cnsout.p, nb * sizeof(CnsOut), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(ctx->h_cns.p, ctx->d_cns.p, cns_total, cudaMemcpyDeviceToHost, st));
-    if (np) CK(cudaMemcpyAsync(ctx->h_aln.p, ctx->d_aln.p, (size_t)np * sizeof(PairAln), cudaMemcpyDeviceToHost, st));
+    CKL(cudaGetLastError());
+    L.counters[FCX_C_KERNEL_LAUNCHES] += 1;
+    CKL(cudaEventRecord(L.ev[6], sh));
+    CKL(cudaMemcpyAsync(L.h_cnsout.p, L.d_cnsout.p, nb * sizeof(CnsOut), cudaMemcpyDeviceToHost, sh));
+    CKL(cudaMemcpyAsync(L.h_cns.p, L.d_cns.p, cns_total, cudaMemcpyDeviceToHost, sh));
+    if (np) CKL(cudaMemcpyAsync(L.h_aln.p, L.d_aln.p, (size_t)np * sizeof(PairAln), cudaMemcpyDeviceToHost, sh));
     if (ctx->want_eqv) {
-        CK(ctx->h_eqv.reserve(cns_total * 4));
-        CK(cudaMemcpyAsync(ctx->h_eqv.p, ctx->d_eqv.p, cns_total * 4, cudaMemcpyDeviceToHost, st));
+        CKL(L.h_eqv.reserve(cns_total * 4));
+        CKL(cudaMemcpyAsync(L.h_eqv.p, L.d_eqv.p, cns_total * 4, cudaMemcpyDeviceToHost, sh));
     }
-    CK(cudaStreamSynchronize(st));
+    CKL(cudaStreamSynchronize(sh));
 
     // ---- collect
-    const CnsOut* co = ctx->h_cnsout.as<CnsOut>();
-    const char* hc = ctx->h_cns.as<char>();
+    const CnsOut* co = L.h_cnsout.as<CnsOut>();
+    const char* hc = L.h_cns.as<char>();
+    uint64_t out_total = 0;
+    for (uint32_t b = 0; b < nb; b++) out_total += (uint64_t)std::max(co[b].len, 0);
+    res.bases.reserve(out_total); res.lens.reserve(nb);
     for (uint32_t b = 0; b < nb; b++) {
         if (co[b].err) {
             char buf[256];
             snprintf(buf, sizeof buf, "consensus kernel error %d in block %u (1: link table overflow, 2: record overflow, 3: no best score (reference asserts, falcon.c:476))",
                      co[b].err, b0 + b);
-            ctx->err = buf; return 3;
+            L.err = buf; return 3;
         }
-        ctx->prof[0] += co[b].deep_positions; ctx->prof[1] += co[b].positions;
-        ctx->prof[2] += (double)co[b].cyc_vote; ctx->prof[3] += (double)co[b].cyc_dp;
-        ctx->prof[4] += (double)co[b].cyc_generic; ctx->prof[5] += (double)co[b].cyc_backtrack;
-        ctx->out_bases.insert(ctx->out_bases.end(), hc + hb[b].cns_off, hc + hb[b].cns_off + co[b].len);
-        ctx->out_off.push_back(ctx->out_bases.size());
+        L.prof[0] += co[b].deep_positions; L.prof[1] += co[b].positions;
+        L.prof[2] += (double)co[b].cyc_vote; L.prof[3] += (double)co[b].cyc_dp;
+        L.prof[4] += (double)co[b].cyc_generic; L.prof[5] += (double)co[b].cyc_backtrack;
+        res.bases.insert(res.bases.end(), hc + hb[b].cns_off, hc + hb[b].cns_off + co[b].len);
+        res.lens.push_back((uint64_t)co[b].len);
         if (ctx->want_eqv) {
-            const int32_t* he = ctx->h_eqv.as<int32_t>();
-            ctx->out_eqv.insert(ctx->out_eqv.end(), he + hb[b].cns_off, he + hb[b].cns_off + co[b].len);
+            const int32_t* he = L.h_eqv.as<int32_t>();
+            res.eqv.insert(res.eqv.end(), he + hb[b].cns_off, he + hb[b].cns_off + co[b].len);
         }
     }
-    const PairAln* hal = ctx->h_aln.as<PairAln>();
+    const PairAln* hal = L.h_aln.as<PairAln>();
     uint64_t cells = 0, steps = 0, cols = 0, accepted = 0;
+    if (ctx->keep_pair_info) res.info.reserve(np);
     for (uint32_t p = 0; p < np; p++) {
         cells += (uint64_t)hal[p].cells; accepted += hal[p].accepted;
         if (hal[p].aligned) steps += (uint64_t)hal[p].dist + 1;
@@ -385,21 +446,20 @@ int run_wave(fcx_ctx* ctx, uint32_t b0, uint32_t b1, const uint32_t* block_off, 
             pi.passed_filter = hr[p].pass; pi.aligned = hal[p].aligned; pi.dist = hal[p].dist;
             pi.aln_size = hal[p].aln_size; pi.q_e = hal[p].q_e; pi.t_e = hal[p].t_e;
             pi.accepted = hal[p].accepted; pi.n_tags = hal[p].n_tags; pi.trace_cells = hal[p].cells;
-            ctx->pair_info.push_back(pi);
+            res.info.push_back(pi);
         }
     }
-    (void)pair_base;
-    ctx->counters[FCX_C_PAIRS] += np; ctx->counters[FCX_C_DP_PAIRS] += dp_pairs;
-    ctx->counters[FCX_C_ACCEPTED] += accepted; ctx->counters[FCX_C_TRACE_CELLS] += cells;
-    ctx->counters[FCX_C_DP_STEPS] += steps; ctx->counters[FCX_C_ALN_COLS] += cols;
-    ctx->counters[FCX_C_SPAN_BASES] += span_bases; ctx->counters[FCX_C_WAVES] += 1;
+    L.counters[FCX_C_PAIRS] += np; L.counters[FCX_C_DP_PAIRS] += dp_pairs;
+    L.counters[FCX_C_ACCEPTED] += accepted; L.counters[FCX_C_TRACE_CELLS] += cells;
+    L.counters[FCX_C_DP_STEPS] += steps; L.counters[FCX_C_ALN_COLS] += cols;
+    L.counters[FCX_C_SPAN_BASES] += span_bases; L.counters[FCX_C_WAVES] += 1;
     float ms;
-    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->times[FCX_T_INDEX] += ms;
-    cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]); ctx->times[FCX_T_RANGE] += ms;
-    cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]); ctx->times[FCX_T_DP] += ms;
-    cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]); ctx->times[FCX_T_TRACEBACK] += ms;
-    cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]); ctx->times[FCX_T_CONSENSUS] += ms;
-    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[6]); ctx->times[FCX_T_TOTAL] += ms;
+    cudaEventElapsedTime(&ms, L.ev[0], L.ev[1]); L.times[FCX_T_INDEX] += ms;
+    cudaEventElapsedTime(&ms, L.ev[1], L.ev[2]); L.times[FCX_T_RANGE] += ms;
+    cudaEventElapsedTime(&ms, L.ev[3], L.ev[4]); L.times[FCX_T_DP] += ms;
+    cudaEventElapsedTime(&ms, L.ev[4], L.ev[5]); L.times[FCX_T_TRACEBACK] += ms;
+    cudaEventElapsedTime(&ms, L.ev[5], L.ev[6]); L.times[FCX_T_CONSENSUS] += ms;
+    cudaEventElapsedTime(&ms, L.ev[0], L.ev[6]); L.times[FCX_T_TOTAL] += ms;
     return 0;
 }
 
@@ -420,25 +480,74 @@ extern "C" int fcx_consensus_blocks(fcx_ctx* ctx, uint32_t n_blocks, const uint3
         for (uint32_t i = block_off[b]; i < block_off[b + 1]; i++)
             if (read_ids[i] >= ctx->n_reads) { ctx->err = "read id outside the uploaded pool"; return 1; }
     }
-    // plan waves from upper bounds (exact sizes are computed per wave after k_range)
-    uint32_t b = 0; uint64_t pair_base = 0;
-    while (b < n_blocks) {
+    // ---- plan waves from upper bounds (exact sizes are computed per wave after k_range).
+    // Aim for >= 2 waves per lane so that stages of different waves overlap, but keep waves large
+    // enough (min_wave_blocks) for the one-warp-per-block consensus kernel to fill the GPU.
+    const int nl = (int)ctx->lanes.size();
+    const int wpl = getenv("FCX_WAVES_PER_LANE") ? std::max(1, atoi(getenv("FCX_WAVES_PER_LANE"))) : 1;
+    uint32_t target = (n_blocks + wpl * nl - 1) / (wpl * nl);
+    target = std::max(target, ctx->min_wave_blocks);
+    target = std::min(target, ctx->max_wave_blocks);
+    const double budget = (double)ctx->arena_budget / nl;
+    std::vector<std::pair<uint32_t, uint32_t>> waves;
+    for (uint32_t b = 0; b < n_blocks;) {
         uint32_t e = b; uint64_t pairs = 0; double bytes = 0;
         while (e < n_blocks) {
             uint32_t lo = block_off[e], hi = block_off[e + 1];
             int slen = ctx->h_len[read_ids[lo]];
-            double bb = (double)KTAB * 4 + (double)slen * (4 + 8 * 12 + 2 * 5 + 2) + 4.0 * slen * (((hi - lo - 1) + 31) & ~31u);
+            double bb = (double)KTAB * 4 + (double)slen * (4 + 8 * 12 + 2 * 5) + 4.0 * slen * (((hi - lo - 1) + 31) & ~31u);
             for (uint32_t i = lo + 1; i < hi; i++) {
                 int rl = ctx->h_len[read_ids[i]];
-                bb += 0.3 * (rl + slen) * 36.0 + 8.0 * (slen + 2) + 128;
+                bb += 0.3 * (std::min(rl, slen) * 2.0) * 36.0 + 8.0 * (std::min(rl, slen) + 2) + 128;
             }
-            if (e > b && (bytes + bb > (double)ctx->arena_budget || pairs + (hi - lo - 1) > ctx->max_wave_pairs ||
-                          e - b >= ctx->max_wave_blocks)) break;
+            if (e > b && (bytes + bb > budget || pairs + (hi - lo - 1) > ctx->max_wave_pairs || e - b >= target)) break;
             bytes += bb; pairs += hi - lo - 1; e++;
         }
-        int rc = run_wave(ctx, b, e, block_off, read_ids, min_cov, min_idt, pair_base);
-        if (rc) return rc;
-        pair_base += pairs; b = e;
+        waves.emplace_back(b, e);
+        b = e;
+    }
+    for (auto& L : ctx->lanes) {
+        memset(L.times, 0, sizeof L.times); memset(L.counters, 0, sizeof L.counters); memset(L.prof, 0, sizeof L.prof);
+        L.err.clear();
+    }
+    std::vector<WaveResult> results(waves.size());
+    std::atomic<size_t> next(0);
+    std::atomic<int> failed(0);
+    auto worker = [&](int li) {
+        cudaSetDevice(ctx->device);
+        Lane& L = ctx->lanes[li];
+        for (;;) {
+            size_t w = next.fetch_add(1);
+            if (w >= waves.size() || failed.load()) break;
+            int rc = run_wave(ctx, L, waves[w].first, waves[w].second, block_off, read_ids, min_cov, min_idt, results[w]);
+            if (rc) { failed.store(rc); break; }
+        }
+    };
+    const int nthreads = (int)std::min<size_t>(waves.size(), (size_t)nl);
+    if (nthreads <= 1) worker(0);
+    else {
+        std::vector<std::thread> th;
+        for (int i = 0; i < nthreads; i++) th.emplace_back(worker, i);
+        for (auto& t : th) t.join();
+    }
+    if (failed.load()) {
+        for (auto& L : ctx->lanes) if (!L.err.empty()) { ctx->err = L.err; break; }
+        return failed.load();
+    }
+    // ---- merge in block order
+    uint64_t total = 0;
+    for (auto& r : results) total += r.bases.size();
+    ctx->out_bases.reserve(total); ctx->out_off.reserve((size_t)n_blocks + 1);
+    for (auto& r : results) {
+        ctx->out_bases.insert(ctx->out_bases.end(), r.bases.begin(), r.bases.end());
+        for (uint64_t l : r.lens) ctx->out_off.push_back(ctx->out_off.back() + l);
+        if (ctx->keep_pair_info) ctx->pair_info.insert(ctx->pair_info.end(), r.info.begin(), r.info.end());
+        if (ctx->want_eqv) ctx->out_eqv.insert(ctx->out_eqv.end(), r.eqv.begin(), r.eqv.end());
+    }
+    for (auto& L : ctx->lanes) {
+        for (int i = 0; i < FCX_T_COUNT; i++) ctx->times[i] += L.times[i];
+        for (int i = 0; i < FCX_C_COUNT; i++) ctx->counters[i] += L.counters[i];
+        for (int i = 0; i < 8; i++) ctx->prof[i] += L.prof[i];
     }
     *out_bases = ctx->out_bases.data();
     *out_off = ctx->out_off.data();
@@ -460,13 +569,17 @@ extern "C" int fcx_last_stats(fcx_ctx* ctx, double* times_ms, uint64_t* counters
 
 extern "C" int fcx_internal_profile(fcx_ctx* ctx, double* out8) { memcpy(out8, ctx->prof, sizeof ctx->prof); return 0; }
 
-// CUDA-event stopwatch on the engine's stream (bench.py brackets its timed region with it)
+// CUDA-event stopwatch (bench.py brackets its timed region with it).  The events are recorded on
+// the engine's main stream; every fcx_* call is synchronous, so all lane work issued between start
+// and stop has completed when stop is recorded.
 extern "C" int fcx_timer_start(fcx_ctx* ctx) {
     CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
     CK(cudaEventRecord(ctx->tev[0], ctx->stream));
     return 0;
 }
 extern "C" int fcx_timer_stop(fcx_ctx* ctx, double* ms) {
+    CK(cudaDeviceSynchronize());
     CK(cudaEventRecord(ctx->tev[1], ctx->stream));
     CK(cudaEventSynchronize(ctx->tev[1]));
     float f = 0;
@@ -480,7 +593,48 @@ extern "C" int fcx_internal_want_eqv(fcx_ctx* ctx, int on) { ctx->want_eqv = on 
 extern "C" int fcx_internal_last_eqv(fcx_ctx* ctx, const int32_t** eqv, uint64_t* n) {
     *eqv = ctx->out_eqv.data(); *n = ctx->out_eqv.size(); return 0;
 }
-extern "C" int fcx_internal_align(fcx_ctx* ctx, const char*, int, const char*, int, int, int, alignment*) {
-    ctx->err = "align(): single-pair GPU entry not implemented yet";
-    return 1;
+
+// single-pair align(): see k_align1 / k_align1_tb
+extern "C" int fcx_internal_align(fcx_ctx* ctx, const char* q, int q_len, const char* t, int t_len,
+                                  int band_tolerance, int get_aln_str, alignment* out) {
+    CK(cudaSetDevice(ctx->device));
+    if (q_len < 0 || t_len < 0 || band_tolerance < 0) { ctx->err = "align(): negative length"; return 1; }
+    if (band_tolerance * 2 + 4 > AL_VRING) { ctx->err = "align(): band_tolerance too large for this build"; return 1; }
+    const long long max_d = (long long)(int)(0.3 * (q_len + t_len));
+    if ((long long)INT_MAX < max_d * (long long)(band_tolerance * 2 + 1) * 2LL) {   // DW_banded.c:158-161
+        ctx->err = "align(): lens are too big (the reference aborts here, DW_banded.c:158-161)"; return 1;
+    }
+    std::vector<char> cat((size_t)q_len + t_len + 1);
+    memcpy(cat.data(), q, q_len); memcpy(cat.data() + q_len, t, t_len);
+    uint64_t off[3] = {0, (uint64_t)q_len, (uint64_t)q_len + t_len};
+    if (int rc = fcx_pool_upload(ctx, cat.data(), off, 2)) return rc;
+    const int rec_words = 1 + (band_tolerance + 1 + 31) / 32 + 1;
+    cudaStream_t st = ctx->stream;
+    CK(ctx->d_trace1.reserve((size_t)(max_d + 1) * rec_words * 4 + 64));
+    CK(ctx->d_path1.reserve((size_t)(max_d / 32 + 2) * 4));
+    CK(ctx->d_aln1.reserve(sizeof(PairAln)));
+    CK(ctx->d_str1.reserve(2 * ((size_t)q_len + t_len + 2)));
+    CK(cudaMemsetAsync(ctx->d_path1.p, 0, (size_t)(max_d / 32 + 2) * 4, st));
+    const uint32_t* pool = ctx->d_pool.as<uint32_t>();
+    k_align1<<<1, 32, 0, st>>>(pool, ctx->h_woff[0], ctx->h_woff[1], q_len, t_len, band_tolerance,
+                               ctx->d_trace1.as<uint32_t>(), rec_words, ctx->d_aln1.as<PairAln>());
+    CK(cudaGetLastError());
+    char* dq = ctx->d_str1.as<char>(); char* dt = dq + (size_t)q_len + t_len + 2;
+    if (get_aln_str > 0) {
+        k_align1_tb<<<1, 1, 0, st>>>(pool, ctx->h_woff[0], ctx->h_woff[1], q_len, t_len, ctx->d_trace1.as<uint32_t>(),
+                                     rec_words, ctx->d_path1.as<uint32_t>(), ctx->d_aln1.as<PairAln>(), dq, dt);
+        CK(cudaGetLastError());
+    }
+    PairAln a;
+    CK(cudaMemcpyAsync(&a, ctx->d_aln1.p, sizeof a, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    out->aln_str_size = 0; out->dist = 0; out->aln_q_s = out->aln_q_e = out->aln_t_s = out->aln_t_e = 0;
+    if (a.aligned) {
+        out->aln_str_size = a.aln_size; out->dist = a.dist; out->aln_q_e = a.q_e; out->aln_t_e = a.t_e;
+        if (get_aln_str > 0 && a.aln_size > 0) {
+            CK(cudaMemcpy(out->q_aln_str, dq, (size_t)a.aln_size, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(out->t_aln_str, dt, (size_t)a.aln_size, cudaMemcpyDeviceToHost));
+        }
+    }
+    return 0;
 }

@@ -708,6 +708,114 @@ __global__ void k_traceback(const BlockDesc* __restrict__ blocks, const PairDesc
     aln[p] = a;
 }
 
+// ------------------------------------------------------------------------------ k_align1 / k_align1_tb
+// The legacy single-pair entry align(q, q_len, t, t_len, band_tolerance, get_aln_str)
+// (DW_banded.c:115-330) with an arbitrary band: one warp, generic chunk loop, V ring of AL_VRING
+// entries, trace records of `rec_words` words per step; then a single-thread traceback that writes
+// the two gapped strings (DW_banded.c:264-319).  API surface for falcon_kit.get_alignment /
+// graph_to_contig.get_aln_data; the consensus throughput path uses k_dp.
+constexpr int AL_VRING = 8192;
+
+__global__ void __launch_bounds__(32)
+k_align1(const uint32_t* __restrict__ pool, uint64_t q_woff, uint64_t t_woff, int q_len, int t_len,
+         int band_tol, uint32_t* __restrict__ trace, int rec_words, PairAln* __restrict__ out) {
+    __shared__ int V[AL_VRING];
+    const int lane = threadIdx.x;
+    const uint32_t* q = pool + q_woff; const uint32_t* t = pool + t_woff;
+    PairAln res; res.aligned = res.dist = res.aln_size = res.q_e = res.t_e = res.k_end = 0;
+    res.accepted = res.t_cnt = res.n_tags = res.cells = 0;
+    const int max_d = (int)(0.3 * (q_len + t_len));
+    const int band_size = band_tol * 2;
+    int best_m = -1, min_k = 0, max_k = 0;
+    bool aligned = false; int end_d = 0, end_k = 0, end_x = 0, end_y = 0;
+    for (int d = 0; d < max_d; d++) {
+        if (max_k - min_k > band_size) break;
+        const int ncell = ((max_k - min_k) >> 1) + 1;
+        const int nch = (ncell + 31) >> 5;
+        uint32_t* rec = trace + (size_t)d * rec_words;
+        if (lane == 0) rec[0] = (uint32_t)min_k;
+        int step_best = best_m;
+        for (int c = 0; c < nch; c++) {
+            const int k = min_k + 2 * (lane + 32 * c);
+            const bool act = k <= max_k;
+            int x = 0, y = 0; bool up = false;
+            if (act) {
+                if (d == 0) up = true;
+                else {
+                    const int vm = V[(k - 1) & (AL_VRING - 1)], vp = V[(k + 1) & (AL_VRING - 1)];
+                    up = (k == min_k) || (k != max_k && vm < vp);
+                    x = up ? vp : vm + 1;
+                }
+                y = x - k;
+                snake(q, t, 0, 0, q_len, t_len, x, y);
+            }
+            const unsigned upb = __ballot_sync(FULL, act && up);
+            if (lane == 0) rec[1 + c] = upb;
+            const unsigned finb = __ballot_sync(FULL, act && (x >= q_len || y >= t_len));
+            if (act) V[k & (AL_VRING - 1)] = x;
+            step_best = max(step_best, __reduce_max_sync(FULL, act ? x + y : INT_MIN));
+            if (finb) {
+                const int fl = __ffs(finb) - 1;
+                aligned = true; end_d = d; end_k = min_k + 2 * (fl + 32 * c);
+                end_x = __shfl_sync(FULL, x, fl); end_y = __shfl_sync(FULL, y, fl);
+                break;
+            }
+        }
+        if (aligned) break;
+        best_m = step_best;
+        __syncwarp();
+        int nmin = INT_MAX, nmax = INT_MIN;
+        const int thr = best_m - band_tol;
+        for (int c = 0; c < nch; c++) {
+            const int k = min_k + 2 * (lane + 32 * c);
+            bool ok = false;
+            if (k <= max_k) { const int x = V[k & (AL_VRING - 1)]; ok = (2 * x - k) >= thr; }
+            const unsigned okb = __ballot_sync(FULL, ok);
+            if (okb) {
+                if (nmin == INT_MAX) nmin = min_k + 2 * (__ffs(okb) - 1 + 32 * c);
+                nmax = min_k + 2 * (31 - __clz(okb) + 32 * c);
+            }
+        }
+        max_k = nmax + 1; min_k = nmin - 1;
+        __syncwarp();
+    }
+    if (aligned) {
+        res.aligned = 1; res.dist = end_d; res.q_e = end_x; res.t_e = end_y; res.k_end = end_k;
+        res.aln_size = (end_x + end_y + end_d) / 2;
+    }
+    if (lane == 0) *out = res;
+}
+
+__global__ void k_align1_tb(const uint32_t* __restrict__ pool, uint64_t q_woff, uint64_t t_woff, int q_len, int t_len,
+                            const uint32_t* __restrict__ trace, int rec_words, uint32_t* __restrict__ path,
+                            const PairAln* __restrict__ alnp, char* __restrict__ q_aln, char* __restrict__ t_aln) {
+    const PairAln a = *alnp;
+    if (!a.aligned) return;
+    const uint32_t* q = pool + q_woff; const uint32_t* t = pool + t_woff;
+    const char ACGT[4] = {'A', 'C', 'G', 'T'};
+    const int D = a.dist;
+    int k = a.k_end;
+    for (int d = D; d >= 1; d--) {
+        const uint32_t* rec = trace + (size_t)d * rec_words;
+        const int idx = (k - (int)rec[0]) >> 1;
+        const uint32_t up = (rec[1 + (idx >> 5)] >> (idx & 31)) & 1u;
+        if (up) path[d >> 5] |= 1u << (d & 31);       // path[] is zeroed by the host
+        k += up ? 1 : -1;
+    }
+    int x = 0, y = 0, pos = 0;
+    for (int d = 0; d <= D; d++) {
+        if (d > 0) {
+            if ((path[d >> 5] >> (d & 31)) & 1u) { q_aln[pos] = '-'; t_aln[pos] = ACGT[base_at(t, y)]; y++; pos++; }
+            else { q_aln[pos] = ACGT[base_at(q, x)]; t_aln[pos] = '-'; x++; pos++; }
+        }
+        while (x < q_len && y < t_len && base_at(q, x) == base_at(t, y)) {
+            const char c = ACGT[base_at(q, x)];
+            q_aln[pos] = c; t_aln[pos] = c; x++; y++; pos++;
+        }
+    }
+    q_aln[pos] = 0; t_aln[pos] = 0;
+}
+
 // ------------------------------------------------------------------------------ k_transpose
 // Per-read entry arrays (read-major, written sequentially by k_traceback) -> per-block
 // position-major pile-up matrix M[i][j] (i = seed position, j = pair index in the block, row

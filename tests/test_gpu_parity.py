@@ -165,3 +165,30 @@ def test_full_size_block_vs_oracle(engine, oracle):
     got = engine.consensus_blocks([b.tolist() for b in S.blocks], 4, 0.70)
     for bi in range(len(S.blocks)):
         assert got[bi] == oracle.generate_consensus(S.block_seqs(bi), 4, 0.70)
+
+
+def test_legacy_align_symbol(oracle):
+    """DWA.align (falcon_kit/falcon_kit.py:111-114) on the GPU: band 150 / 100 / 1500, with and
+    without alignment strings, aligned and band-failure cases."""
+    from falcon_b200 import binding
+    lib = binding.lib()
+    rng = np.random.default_rng(17)
+    g = synth.random_codes(7000, rng)
+    a = synth.codes_to_bytes(synth.add_errors(g[200:6800], rng))
+    b = synth.codes_to_bytes(synth.add_errors(g[300:6900], rng))
+    unrelated = synth.codes_to_bytes(synth.random_codes(3000, rng))
+    cases = [(a[100:], b, 150, 1), (a[100:], b, 100, 0), (a[100:], b, 1500, 1), (a[:2500], unrelated, 150, 1),
+             (a[:300], a[:300], 150, 1)]
+    for q, t, band, want_str in cases:
+        p = lib.align(q, len(q), t, len(t), band, want_str)
+        got = dict(n=p[0].aln_str_size, dist=p[0].dist, qe=p[0].aln_q_e, te=p[0].aln_t_e,
+                   qs=p[0].aln_q_s, ts=p[0].aln_t_s)
+        if want_str and got["n"] > 0:
+            got["qa"] = C.string_at(p[0].q_aln_str, got["n"]); got["ta"] = C.string_at(p[0].t_aln_str, got["n"])
+        lib.free_alignment(p)
+        o = oracle.align(q, t, band)
+        assert (got["n"], got["qs"], got["ts"]) == (o["aln_str_size"], 0, 0)
+        if o["aln_str_size"] > 0:
+            assert (got["dist"], got["qe"], got["te"]) == (o["dist"], o["q_e"], o["t_e"])
+            if want_str:
+                assert got["qa"] == o["q_aln"] and got["ta"] == o["t_aln"]

@@ -30,6 +30,7 @@ def main():
                        block_stride=max(1, n_reads // a.blocks))
     print("workload: %d blocks, %d pairs (%.1fs)" % (len(S.blocks), S.n_pairs, time.time() - t0), flush=True)
     eng = Engine(0)
+    eng.set_option("pair_info", 0)
     eng.upload_pool(S.pool)
     blocks = [b.tolist() for b in S.blocks]
     L = lib()
