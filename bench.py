@@ -156,7 +156,8 @@ def main():
     ap.add_argument("--genome", type=int, default=4_600_000)
     ap.add_argument("--read-len", type=int, default=15000)
     ap.add_argument("--cov", type=float, default=50.0)
-    ap.add_argument("--blocks", type=int, default=2048, help="seed blocks per rank per step (0 = every read is a seed)")
+    ap.add_argument("--blocks", type=int, default=0,
+                    help="seed blocks per rank per step (0 = the whole set: every read is a seed, ~15.3k blocks)")
     ap.add_argument("--max-n-read", type=int, default=200)
     ap.add_argument("--min-cov", type=int, default=4)
     ap.add_argument("--min-idt", type=float, default=0.70)
@@ -306,8 +307,17 @@ def main():
     bytes_cns = 2 * 8.0 * A + seed_bases
     alg = {"dp": bytes_dp, "consensus": bytes_cns, "traceback": 4.0 * E / 8 + 8.0 * A, "range": SP / 4.0, "index": seed_bases * 4}
     ach = alg.get(dom, 0.0) / (kms[dom] / 1e3) / 1e9 if kms[dom] > 0 else 0.0
+    traffic = None
+    try:   # dram__bytes_read+write per launch of the dominant kernel, from the committed ncu capture
+        prof = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))
+        k = prof.get("k_" + dom)
+        if k:
+            traffic = {"bytes_per_launch": k["dram_bytes"], "pairs_in_launch": k.get("pairs"),
+                       "bytes_per_pair": k["dram_bytes"] / max(1, k.get("pairs", 1)), "source": "profiles/ncu_summary.json"}
+    except Exception:
+        pass
     roofline = {"kernel": "k_" + dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                "frac": ach / peak, "traffic": None,
+                "frac": ach / peak, "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
                 "kernel_ms_per_step": kms, "algorithmic_bytes_per_step": alg[dom],
                 "dp_kernel": {"achieved": bytes_dp / (kms["dp"] / 1e3) / 1e9 if kms["dp"] > 0 else 0.0,

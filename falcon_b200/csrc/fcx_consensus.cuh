@@ -37,16 +37,17 @@ constexpr int LINK_CAP = 512;     // generic path: distinct (delta, base, link) 
 constexpr int LVL = 255 * 5;      // (delta, base) slots of one position
 constexpr int RCAP = 160;         // accepted reads whose metadata is cached in shared memory
 constexpr int NCHR = 8;           // row chunks (of 32 pairs) pipelined through registers
-constexpr int FJ = 3;             // fast path: longest insertion run / predecessor delta
+constexpr int FJ = 7;             // fast path: longest insertion run / predecessor delta
 constexpr int T0W = 1 + (FJ + 1) * 5;            // links of a delta-0 column: START + (pd, pb)
 constexpr int DENSE0 = 2 * T0W;                  // two live delta-0 columns: seed base, '-'
 constexpr int DENSE = DENSE0 + FJ * 20;          // + FJ insertion levels x 4 bases x 5 preds
-constexpr int DENSE_PAD = 128;
+constexpr int DENSE_PAD = 256;
 constexpr int SLV = 8 * 5;                       // (delta, base) slots kept in shared memory
 constexpr int BTW = 160;                         // backtrack window (records)
 constexpr int NOFIRST = 0x7fffffff;              // "no voter yet" in the dense first[] table
 static_assert(DENSE <= DENSE_PAD, "dense table too small");
-static_assert(T0W <= 32, "level-0 links must fit one warp");
+static_assert(T0W <= 64, "level-0 links: at most two per lane");
+static_assert((FJ + 1) * 5 <= SLV, "fast-path levels must live in the shared-memory tables");
 
 struct ReadMeta { uint64_t q_woff; uint32_t xam_off_lo, xam_off_hi; int32_t t_start, t_cnt, q_s; int32_t pad; };
 
@@ -76,7 +77,8 @@ __global__ void __launch_bounds__(CNS_WARPS * 32)
 k_consensus(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, const PairDesc* __restrict__ pairs,
             const PairRange* __restrict__ ranges, const PairAlloc* __restrict__ allocs,
             const PairAln* __restrict__ aln, const uint32_t* __restrict__ pool,
-            const uint32_t* __restrict__ xam_arena, const uint32_t* __restrict__ m_arena,
+            const uint32_t* __restrict__ xam_arena, const uint32_t* __restrict__ ent_arena,
+            const uint32_t* __restrict__ m_arena,
             CnsRec* __restrict__ rec_arena, int32_t* __restrict__ lvl_scratch,
             ReadMeta* __restrict__ meta_scratch, uint64_t meta_stride,
             char* __restrict__ cns_arena, int32_t* __restrict__ eqv_arena, unsigned min_cov,
@@ -197,7 +199,7 @@ k_consensus(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, const PairD
                     const int pn = ent_nins(ep);
                     dpl = dpl || pn > FJ;
                     const int pb = pn > 0 ? ent_ins(ep, (pn - 1) & 7) : ((ep & ENT_MATCH) ? Sp : 4);
-                    l0 = 1 + (pn & 3) * 5 + pb;
+                    l0 = 1 + (pn & 7) * 5 + pb;
                 }
                 const int idx0 = (m ? 0 : T0W) + l0;
                 cov_lane += act ? 1 : 0;
@@ -208,13 +210,13 @@ k_consensus(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, const PairD
                 maj_cnt += __popc(majb);
                 if (majb && maj_first == NOFIRST) maj_first = c * 32 + __ffs(majb) - 1;
                 if (vote && idx0 != idx_maj) { atomicAdd(&sm.cnt[idx0], 1); atomicMin(&sm.first[idx0], ai); }
-#pragma unroll
-                for (int lev = 1; lev <= FJ; lev++) {
-                    if (vote && nins >= lev) {
+                if (vote && nins >= 1) {                       // insertion tags (few lanes: divergent is fine)
+                    int pb = b0;
+                    for (int lev = 1; lev <= nins; lev++) {
                         const int bb = ent_ins(ec, lev - 1);
-                        const int pb = (lev == 1) ? b0 : ent_ins(ec, lev - 2);
                         const int idx = DENSE0 + (lev - 1) * 20 + bb * 5 + pb;
                         atomicAdd(&sm.cnt[idx], 1); atomicMin(&sm.first[idx], ai);
+                        pb = bb;
                     }
                 }
             }
@@ -231,28 +233,40 @@ k_consensus(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, const PairD
             if (coverage != 0) {
                 // =========================================================== fast DP
                 // all (j <= maxd, kk) slots start dead (score -1, record 0)
-                if (lane < (maxd + 1) * 5) { tc.s_sc[lane] = -2; tc.s_rc[lane] = 0; }
-                // ---- level 0: the two live columns (seed base Si, '-') side by side; lane = link
-                int cA = 0, fA = NOFIRST, cB = 0, fB = NOFIRST, ps = 0, prc = -1;
-                if (lane < T0W) {
-                    cA = sm.cnt[lane]; fA = sm.first[lane]; cB = sm.cnt[T0W + lane]; fB = sm.first[T0W + lane];
-                    if (cA) { sm.cnt[lane] = 0; sm.first[lane] = NOFIRST; }
-                    if (cB) { sm.cnt[T0W + lane] = 0; sm.first[T0W + lane] = NOFIRST; }
-                    if (lane > 0) { ps = tp.s_sc[lane - 1]; prc = tp.s_rc[lane - 1]; }
+                for (int e = lane; e < (maxd + 1) * 5; e += 32) { tc.s_sc[e] = -2; tc.s_rc[e] = 0; }
+                // ---- level 0: the two live columns (seed base Si = A, '-' = B) side by side; each
+                // lane owns links `lane` and `lane + 32` (T0W = 41 candidate links per column)
+                int cA0 = 0, fA0 = NOFIRST, cB0 = 0, fB0 = NOFIRST, ps0 = 0, pr0 = -1;
+                int cA1 = 0, fA1 = NOFIRST, cB1 = 0, fB1 = NOFIRST, ps1 = 0, pr1 = -1;
+                {
+                    cA0 = sm.cnt[lane]; fA0 = sm.first[lane]; cB0 = sm.cnt[T0W + lane]; fB0 = sm.first[T0W + lane];
+                    if (cA0) { sm.cnt[lane] = 0; sm.first[lane] = NOFIRST; }
+                    if (cB0) { sm.cnt[T0W + lane] = 0; sm.first[T0W + lane] = NOFIRST; }
+                    if (lane > 0) { ps0 = tp.s_sc[lane - 1]; pr0 = tp.s_rc[lane - 1]; }
+                    const int l1 = lane + 32;
+                    if (l1 < T0W) {
+                        cA1 = sm.cnt[l1]; fA1 = sm.first[l1]; cB1 = sm.cnt[T0W + l1]; fB1 = sm.first[T0W + l1];
+                        if (cA1) { sm.cnt[l1] = 0; sm.first[l1] = NOFIRST; }
+                        if (cB1) { sm.cnt[T0W + l1] = 0; sm.first[T0W + l1] = NOFIRST; }
+                        ps1 = tp.s_sc[l1 - 1]; pr1 = tp.s_rc[l1 - 1];
+                    }
                 }
                 __syncwarp();
-                const bool vA = cA > 0, vB = cB > 0;
-                const int sA = vA ? 2 * cA - coverage + ps : INT_MIN;
-                const int sB = vB ? 2 * cB - coverage + ps : INT_MIN;
-                const int mxA = __reduce_max_sync(FULL, sA), mxB = __reduce_max_sync(FULL, sB);
-                const int fmA = __reduce_min_sync(FULL, (vA && sA == mxA) ? fA : NOFIRST);
-                const int fmB = __reduce_min_sync(FULL, (vB && sB == mxB) ? fB : NOFIRST);
-                const unsigned wbA = __ballot_sync(FULL, vA && sA == mxA && fA == fmA);
-                const unsigned wbB = __ballot_sync(FULL, vB && sB == mxB && fB == fmB);
-                const int ckA = __popc(__ballot_sync(FULL, vA && fA < fmA));
-                const int ckB = __popc(__ballot_sync(FULL, vB && fB < fmB));
-                const int prA = __shfl_sync(FULL, prc, wbA ? __ffs(wbA) - 1 : 0);
-                const int prB = __shfl_sync(FULL, prc, wbB ? __ffs(wbB) - 1 : 0);
+                const int sA0 = cA0 > 0 ? 2 * cA0 - coverage + ps0 : INT_MIN, sA1 = cA1 > 0 ? 2 * cA1 - coverage + ps1 : INT_MIN;
+                const int sB0 = cB0 > 0 ? 2 * cB0 - coverage + ps0 : INT_MIN, sB1 = cB1 > 0 ? 2 * cB1 - coverage + ps1 : INT_MIN;
+                const int mxA = __reduce_max_sync(FULL, max(sA0, sA1)), mxB = __reduce_max_sync(FULL, max(sB0, sB1));
+                const int fcA = min((cA0 > 0 && sA0 == mxA) ? fA0 : NOFIRST, (cA1 > 0 && sA1 == mxA) ? fA1 : NOFIRST);
+                const int fcB = min((cB0 > 0 && sB0 == mxB) ? fB0 : NOFIRST, (cB1 > 0 && sB1 == mxB) ? fB1 : NOFIRST);
+                const int fmA = __reduce_min_sync(FULL, fcA), fmB = __reduce_min_sync(FULL, fcB);
+                const unsigned wbA = __ballot_sync(FULL, fcA == fmA && fmA != NOFIRST);
+                const unsigned wbB = __ballot_sync(FULL, fcB == fmB && fmB != NOFIRST);
+                const int ckA = __popc(__ballot_sync(FULL, cA0 > 0 && fA0 < fmA)) + __popc(__ballot_sync(FULL, cA1 > 0 && fA1 < fmA));
+                const int ckB = __popc(__ballot_sync(FULL, cB0 > 0 && fB0 < fmB)) + __popc(__ballot_sync(FULL, cB1 > 0 && fB1 < fmB));
+                // the winning lane hands over the predecessor record of its winning link
+                const int prA_l = (cA0 > 0 && sA0 == mxA && fA0 == fmA) ? pr0 : pr1;
+                const int prB_l = (cB0 > 0 && sB0 == mxB && fB0 == fmB) ? pr0 : pr1;
+                const int prA = __shfl_sync(FULL, prA_l, wbA ? __ffs(wbA) - 1 : 0);
+                const int prB = __shfl_sync(FULL, prB_l, wbB ? __ffs(wbB) - 1 : 0);
 #pragma unroll
                 for (int col = 0; col < 2; col++) {
                     const int mx = col ? mxB : mxA;
@@ -328,15 +342,18 @@ k_consensus(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, const PairD
                 int m = 0, x = 0, nins = 0, b0 = 0; uint32_t lk0 = 0;
                 const uint32_t* qr = pool; int qs = 0;
                 if (act) {
-                    const uint32_t* xam = xam_arena + (((uint64_t)rm.xam_off_hi << 32) | rm.xam_off_lo);
-                    const uint32_t c = xam[y], nx = xam[y + 1];
-                    m = c & 1; x = (int)(c >> 1); nins = (int)(nx >> 1) - x - m;
+                    const uint64_t xo = ((uint64_t)rm.xam_off_hi << 32) | rm.xam_off_lo;
+                    const uint32_t* xam = xam_arena + xo;
+                    const uint32_t* ent = ent_arena + xo;
+                    const uint32_t e = ent[y];
+                    m = (e & ENT_MATCH) ? 1 : 0; nins = ent_nins(e);
+                    x = xam_lookup(xam, ent, y);
                     b0 = m ? Si : 4;
                     qr = pool + rm.q_woff; qs = rm.q_s;
                     if (y == 0) lk0 = 0x1fffu;                         // (p_t_pos = -1, 0, '.')
                     else {
-                        const uint32_t pv = xam[y - 1];
-                        const int pm = pv & 1, px = (int)(pv >> 1), pn = x - px - pm;
+                        const uint32_t pe = ent[y - 1];
+                        const int pm = (pe & ENT_MATCH) ? 1 : 0, pn = ent_nins(pe);
                         const int pb = pn > 0 ? base_at(qr, qs + x - 1) : (pm ? Sp : 4);
                         lk0 = ((uint32_t)pn << 3) | (uint32_t)pb;
                     }

@@ -353,8 +353,8 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
         }
     }
     CKL(L.d_trace.reserve(trace_recs * TRACE_REC_WORDS * 4 + 64));
-    CKL(L.d_xam.reserve(xam_n * 4 + 64));
-    CKL(L.d_ent.reserve(xam_n * 4 + 64));
+    CKL(L.d_xam.reserve(xam_n * 4 + 128));
+    CKL(L.d_ent.reserve(xam_n * 4 + 128));
     CKL(L.d_path.reserve(path_w * 4 + 64));
     CKL(L.d_M.reserve(m_total * 4 + 64));
     if (np) CKL(cudaMemcpyAsync(L.d_allocs.p, ha.data(), (size_t)np * sizeof(PairAlloc), cudaMemcpyHostToDevice, st));
@@ -370,6 +370,11 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
     CKL(cudaEventRecord(L.ev[4], st));
     // ---- traceback + transpose
     if (np) {
+        const uint64_t n16 = (xam_n + 3) / 4 + 1;
+        k_fill32<<<(unsigned)std::min<uint64_t>((n16 + 255) / 256, (uint64_t)ctx->sm_count * 16), 256, 0, st>>>(
+            L.d_ent.as<uint4>(), n16, ENT_PLAIN);
+        CKL(cudaGetLastError());
+        L.counters[FCX_C_KERNEL_LAUNCHES] += 1;
         k_traceback<<<(np + 127) / 128, 128, 0, st>>>(
             L.d_blocks.as<BlockDesc>(), L.d_pairs.as<PairDesc>(), L.d_ranges.as<PairRange>(),
             L.d_allocs.as<PairAlloc>(), np, pool, L.d_trace.as<uint32_t>(), L.d_path.as<uint32_t>(),
@@ -394,7 +399,7 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
         kfn<<<cns_grid, CNS_WARPS * 32, 0, sh>>>(
             L.d_blocks.as<BlockDesc>(), nb, L.d_pairs.as<PairDesc>(), L.d_ranges.as<PairRange>(),
             L.d_allocs.as<PairAlloc>(), L.d_aln.as<PairAln>(), pool, L.d_xam.as<uint32_t>(),
-            L.d_M.as<uint32_t>(), L.d_recs.as<CnsRec>(), L.d_lvl.as<int32_t>(),
+            L.d_ent.as<uint32_t>(), L.d_M.as<uint32_t>(), L.d_recs.as<CnsRec>(), L.d_lvl.as<int32_t>(),
             L.d_meta.as<ReadMeta>(), (uint64_t)max_np, L.d_cns.as<char>(), L.d_eqv.as<int32_t>(), min_cov,
             L.d_cnsout.as<CnsOut>());
     }

@@ -455,16 +455,13 @@ __device__ __forceinline__ void snake(const uint32_t* __restrict__ q, const uint
 struct DpCell { int x, y; bool up; };
 
 // predecessor choice of one cell (DW_banded.c:190-197); inactive lanes get a harmless (0,0)
-__device__ __forceinline__ DpCell dp_pick(const int* V, int d, int k, int min_k, int max_k, bool act) {
-    DpCell c; c.up = false; c.x = 0; c.y = 0;
-    if (d == 0) { c.up = act; }                             // V[k+1] is calloc'd 0
-    else {
-        const int vm = V[(k - 1) & (VRING - 1)], vp = V[(k + 1) & (VRING - 1)];
-        const bool up = (k == min_k) || (k != max_k && vm < vp);
-        c.up = act && up;
-        c.x = act ? (up ? vp : vm + 1) : 0;
-        c.y = act ? c.x - k : 0;
-    }
+__device__ __forceinline__ DpCell dp_pick(const int* V, int k, int min_k, int max_k, bool act) {
+    DpCell c;
+    const int vm = V[(k - 1) & (VRING - 1)], vp = V[(k + 1) & (VRING - 1)];
+    const bool up = (k == min_k) || (k != max_k && vm < vp);
+    c.up = act && up;
+    c.x = act ? (up ? vp : vm + 1) : 0;
+    c.y = act ? c.x - k : 0;
     return c;
 }
 
@@ -484,7 +481,9 @@ __device__ __forceinline__ int snake16(const uint32_t* __restrict__ q, const uin
 __device__ __forceinline__ DpCell dp_cell(const int* V, int d, int k, int min_k, int max_k,
                                           const uint32_t* __restrict__ q, const uint32_t* __restrict__ t,
                                           int qs, int ts, int q_len, int t_len) {
-    DpCell c = dp_pick(V, d, k, min_k, max_k, true);
+    DpCell c;
+    if (d == 0) { c.up = true; c.x = 0; c.y = -k; }        // V[k+1] is calloc'd 0
+    else c = dp_pick(V, k, min_k, max_k, true);
     snake(q, t, qs, ts, q_len, t_len, c.x, c.y);
     return c;
 }
@@ -506,14 +505,25 @@ k_dp(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs,
     const uint32_t* q = pool + pd.read_woff;
     const uint32_t* t = pool + blocks[pd.block].seed_woff;
     const int qs = rg.s1, ts = rg.s2, q_len = rg.e1 - rg.s1, t_len = rg.e2 - rg.s2;
-    const int max_d = (int)(0.3 * (q_len + t_len));           // DW_banded.c:149
+    int max_d = (int)(0.3 * (q_len + t_len));                 // DW_banded.c:149
+    asm volatile("" : "+r"(max_d));     // keep the FP64 conversion out of the d loop (ptxas rematerialises it)
     const int band_size = BAND_TOL * 2;                        // :151
     int* V = s_V[wib];
     uint32_t* trace = trace_arena + allocs[p].trace_off * TRACE_REC_WORDS;
 
     int best_m = -1, min_k = 0, max_k = 0, cells = 0;
     bool aligned = false; int end_d = 0, end_k = 0, end_x = 0, end_y = 0;
-    for (int d = 0; d < max_d; d++) {
+    // ---- d = 0 peeled: the single cell k = 0 starts at (0,0) (V is calloc'd, DW_banded.c:153,190-192)
+    if (max_d > 0) {
+        int x = 0, y = 0;
+        snake(q, t, qs, ts, q_len, t_len, x, y);               // same on every lane
+        if (lane == 0) { trace[0] = 0u; trace[1] = 1u; }
+        cells = 1;
+        if (x >= q_len || y >= t_len) { aligned = true; end_x = x; end_y = y; }
+        else { if (lane == 0) V[0] = x; best_m = x + y; min_k = -1; max_k = 1; }
+        __syncwarp();
+    }
+    for (int d = 1; d < max_d && !aligned; d++) {
         if (max_k - min_k > band_size) break;                  // :184-186
         const int ncell = ((max_k - min_k) >> 1) + 1;
         uint32_t* rec = trace + (size_t)d * TRACE_REC_WORDS;
@@ -522,11 +532,11 @@ k_dp(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs,
             const bool two = ncell > 32;
             const int k0 = min_k + 2 * lane, k1 = k0 + 64;
             const bool a0 = k0 <= max_k, a1 = two && k1 <= max_k;
-            DpCell c0 = dp_pick(V, d, k0, min_k, max_k, a0), c1;
+            DpCell c0 = dp_pick(V, k0, min_k, max_k, a0), c1;
             c1.x = c1.y = 0; c1.up = false;
             int n0 = snake16(q, t, qs, ts, q_len, t_len, a0, c0.x, c0.y), n1 = 0;
             if (two) {
-                c1 = dp_pick(V, d, k1, min_k, max_k, a1);
+                c1 = dp_pick(V, k1, min_k, max_k, a1);
                 n1 = snake16(q, t, qs, ts, q_len, t_len, a1, c1.x, c1.y);
             }
             while (__ballot_sync(FULL, n0 == 16 || n1 == 16)) {      // long snakes: rare
@@ -535,7 +545,10 @@ k_dp(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs,
             }
             const unsigned up0 = __ballot_sync(FULL, c0.up);
             const unsigned up1 = two ? __ballot_sync(FULL, c1.up) : 0u;
-            if (lane < 3) rec[lane] = lane == 0 ? (uint32_t)min_k : (lane == 1 ? up0 : up1);
+            if (lane == 0) {
+                *reinterpret_cast<uint2*>(rec) = make_uint2((uint32_t)min_k, up0);
+                if (two) rec[2] = up1;
+            }
             const unsigned fin0 = __ballot_sync(FULL, a0 && (c0.x >= q_len || c0.y >= t_len));     // :220
             const unsigned fin1 = two ? __ballot_sync(FULL, a1 && (c1.x >= q_len || c1.y >= t_len)) : 0u;
             if (fin0 | fin1) {                                  // first k in ascending order wins
@@ -626,6 +639,7 @@ k_dp(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs,
 // (falcon.c:138,150-152): t_cnt is cut there and exactly 254 insertion tags remain.
 constexpr uint32_t ENT_VALID = 0x80000000u;
 constexpr uint32_t ENT_MATCH = 0x40000000u;
+constexpr uint32_t ENT_PLAIN = 0xC0000000u;    // VALID | MATCH, no insertions
 constexpr int ENT_INS_INLINE = 11;
 __device__ __forceinline__ int ent_nins(uint32_t e) { return (int)((e >> 22) & 0xffu); }
 __device__ __forceinline__ int ent_ins(uint32_t e, int k) { return (int)((e >> (2 * k)) & 3u); }
@@ -656,56 +670,87 @@ __global__ void k_traceback(const BlockDesc* __restrict__ blocks, const PairDesc
     uint32_t acc = 0;
     for (int d = D; d >= 1; d--) {
         const uint32_t* rec = trace + (size_t)d * TRACE_REC_WORDS;
-        int idx = (k - (int)rec[0]) >> 1;
-        uint32_t up = (rec[1 + (idx >> 5)] >> (idx & 31)) & 1u;
+        const uint2 hd = __ldg(reinterpret_cast<const uint2*>(rec));       // {min_k, first ballot word}
+        const int idx = (k - (int)hd.x) >> 1;
+        const uint32_t w = idx < 32 ? hd.y : __ldg(rec + 1 + (idx >> 5));
+        const uint32_t up = (w >> (idx & 31)) & 1u;
         acc |= up << (d & 31);
         if ((d & 31) == 0 || d == 1) { path[d >> 5] = acc; acc = 0; }
         k += up ? 1 : -1;
     }
-    // (2) forwards
+    // (2) forwards.  ent[] was pre-filled with ENT_PLAIN (= a match column without insertions), so
+    // only the other columns are written: target-only columns and columns followed by query-only
+    // columns.  xam[] (query index at the column, used by the rare generic consensus path to fetch
+    // inserted bases beyond the 11 inline ones) is written at exactly those columns and at y = 0;
+    // xam_lookup() reconstructs it anywhere else.
     int x = 0, y = 0, run = 0, t_cnt = -1, n_match_cols = 0;
-    uint32_t pend = 0; int pend_y = -1;          // entry of the last target column, still open
+    uint32_t pend = 0; int pend_y = -1, pend_x = 0;   // entry of the last target column, still open
     uint32_t pw = 0;
+    xam[0] = 1u;                                      // column 0 is always a match at x = 0
     for (int d = 0; d <= D; d++) {
         if (d > 0) {
             if ((d & 31) == 0 || d == 1) pw = path[d >> 5];
             if ((pw >> (d & 31)) & 1u) {              // target-only column
-                if (pend_y >= 0) ent[pend_y] = pend | ((uint32_t)run << 22);
-                xam[y] = (uint32_t)x << 1; pend = ENT_VALID; pend_y = y; y++; run = 0;
+                if (pend_y >= 0 && (run > 0 || !(pend & ENT_MATCH))) {
+                    ent[pend_y] = pend | ((uint32_t)run << 22);
+                    xam[pend_y] = ((uint32_t)pend_x << 1) | ((pend & ENT_MATCH) ? 1u : 0u);
+                }
+                pend = ENT_VALID; pend_y = y; pend_x = x; y++; run = 0;
             } else {                                  // query-only column
                 if (run < ENT_INS_INLINE) pend |= (uint32_t)base_at(q, qs + x) << (2 * run);
                 x++; run++;
                 if (run == 255) {            // the 255th consecutive query-only column: tags stop before it
                     t_cnt = y;               // target positions 0..y-1 carry tags
-                    xam[y] = (uint32_t)(x - 1) << 1;   // keeps n_ins(y-1) == 254
-                    run = 254;
+                    x--; run = 254;          // exactly 254 insertion tags remain on column y-1
                     break;
                 }
             }
         }
-        // snake
+        // snake: no per-base stores, interior match columns stay ENT_PLAIN
+        int adv = 0;
         for (;;) {
-            int rem = min(q_len - x, t_len - y);
+            int rem = min(q_len - x - adv, t_len - y - adv);
             if (rem <= 0) break;
-            uint32_t diff = fetch16(q, qs + x) ^ fetch16(t, ts + y);
+            uint32_t diff = fetch16(q, qs + x + adv) ^ fetch16(t, ts + y + adv);
             int n = diff ? (__ffs(diff) - 1) >> 1 : 16;
             n = min(n, rem);
-            if (n > 0) {
-                if (pend_y >= 0) ent[pend_y] = pend | ((uint32_t)run << 22);
-                for (int j = 0; j < n; j++) xam[y + j] = ((uint32_t)(x + j) << 1) | 1u;
-                for (int j = 0; j + 1 < n; j++) ent[y + j] = ENT_VALID | ENT_MATCH;
-                pend = ENT_VALID | ENT_MATCH; pend_y = y + n - 1; run = 0;
-            }
-            x += n; y += n; n_match_cols += n;
+            adv += n;
             if (n < 16) break;
         }
+        if (adv > 0) {
+            if (pend_y >= 0 && (run > 0 || !(pend & ENT_MATCH))) {
+                ent[pend_y] = pend | ((uint32_t)run << 22);
+                xam[pend_y] = ((uint32_t)pend_x << 1) | ((pend & ENT_MATCH) ? 1u : 0u);
+            }
+            x += adv; y += adv; n_match_cols += adv;
+            pend = ENT_PLAIN; pend_y = y - 1; pend_x = x - 1; run = 0;
+        }
     }
-    if (pend_y >= 0) ent[pend_y] = pend | ((uint32_t)run << 22);
-    if (t_cnt < 0) { t_cnt = y; xam[y] = (uint32_t)x << 1; }
+    if (pend_y >= 0 && (run > 0 || !(pend & ENT_MATCH))) {
+        ent[pend_y] = pend | ((uint32_t)run << 22);
+        xam[pend_y] = ((uint32_t)pend_x << 1) | ((pend & ENT_MATCH) ? 1u : 0u);
+    }
+    if (t_cnt < 0) t_cnt = y;
     a.t_cnt = t_cnt;
-    // tagged columns = target columns + query-only columns among them
-    a.n_tags = t_cnt + ((int)(xam[t_cnt] >> 1) - n_match_cols);
+    a.n_tags = t_cnt + (x - n_match_cols);            // target columns + query-only columns among them
     aln[p] = a;
+}
+
+// query index x at target column y of one read: nearest explicitly recorded column at or before y
+// (every non-plain column and column 0 carry xam), then one base per plain match column.
+__device__ __forceinline__ int xam_lookup(const uint32_t* __restrict__ xam, const uint32_t* __restrict__ ent, int y) {
+    int j = y;
+    while (j > 0 && ent[j] == ENT_PLAIN) j--;
+    const int xj = (int)(xam[j] >> 1);
+    if (j == y) return xj;
+    const uint32_t e = ent[j];
+    return xj + ((e & ENT_MATCH) ? 1 : 0) + ent_nins(e) + (y - j - 1);
+}
+
+// ------------------------------------------------------------------------------ k_fill32
+__global__ void k_fill32(uint4* __restrict__ dst, uint64_t n16, uint32_t v) {
+    const uint4 val = make_uint4(v, v, v, v);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (uint64_t)gridDim.x * blockDim.x) dst[i] = val;
 }
 
 // ------------------------------------------------------------------------------ k_align1 / k_align1_tb

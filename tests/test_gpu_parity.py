@@ -92,6 +92,34 @@ def test_low_complexity_match_list_overflow(engine, oracle):
     assert got == want
 
 
+def test_long_insertions_take_the_generic_consensus_path(engine, oracle):
+    """Reads carrying 9..20-base insertions (longer than the dense fast path's 7 and than the 11
+    bases kept inline in the pile-up entries) must vote through the generic link-list path and the
+    xam_lookup() reconstruction, bit-exactly."""
+    rng = np.random.default_rng(23)
+    g = synth.random_codes(8000, rng)
+    seed = synth.codes_to_bytes(g)
+    reads = []
+    for r in range(14):
+        x = synth.add_errors(g, rng, 0.03, 0.02, 0.01)
+        parts, pos = [], 0
+        for cut in sorted(rng.integers(300, len(x) - 300, size=6)):
+            parts.append(x[pos:cut]); parts.append(synth.random_codes(int(rng.integers(9, 21)), rng)); pos = cut
+        parts.append(x[pos:])
+        reads.append(synth.codes_to_bytes(np.concatenate(parts)))
+    # two reads share one identical long insertion so that deep columns get real votes
+    ins = synth.random_codes(15, rng)
+    for r in (3, 4, 5):
+        x = np.frombuffer(reads[r], dtype=np.uint8)
+        reads[r] = reads[r][:4000] + synth.codes_to_bytes(ins) + reads[r][4000:]
+    seqs = [seed, seed] + reads
+    for min_cov in (0, 3):
+        got = engine.generate_consensus(seqs, min_cov, 0.70)
+        assert got == oracle.generate_consensus(seqs, min_cov, 0.70)
+    info = engine.pair_info()
+    assert sum(i.accepted for i in info) >= 10
+
+
 def test_rejects_non_acgt(engine):
     from falcon_b200.binding import EngineError
     with pytest.raises(EngineError):
