@@ -152,20 +152,19 @@ k_consensus(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, const PairD
 
     const uint32_t* Mb = m_arena + bd.m_off;
     const int RB = (int)bd.rb_pad;
-    const bool rows_in_regs = RB <= NCHR * 32;       // else every position takes the generic path
     long long cyc_vote = 0, cyc_dp = 0, cyc_generic = 0, cyc_backtrack = 0; int n_deep = 0;
 
     uint32_t ecv[NCHR], epv[NCHR], ecn[NCHR];
 #pragma unroll
     for (int c = 0; c < NCHR; c++) {
         epv[c] = 0;        // no read covers i_lo - 1
-        ecv[c] = (rows_in_regs && c * 32 < RB && i_lo < i_hi) ? __ldg(Mb + (size_t)i_lo * RB + c * 32 + lane) : 0u;
+        ecv[c] = (c * 32 < RB && i_lo < i_hi) ? __ldg(Mb + (size_t)i_lo * RB + c * 32 + lane) : 0u;
         ecn[c] = 0;
     }
 
     for (int i = i_lo; i < i_hi; i++) {
         // prefetch row i+1 (consumed next iteration)
-        if (rows_in_regs && i + 1 < i_hi) {
+        if (i + 1 < i_hi) {
 #pragma unroll
             for (int c = 0; c < NCHR; c++) if (c * 32 < RB) ecn[c] = __ldg(Mb + (size_t)(i + 1) * RB + c * 32 + lane);
         }
@@ -174,7 +173,7 @@ k_consensus(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, const PairD
         const LvlTab& tp = cur ? tabA : tabB;
         const LvlTab& tc = cur ? tabB : tabA;
         int coverage = 0, maxd = 0;
-        bool deep = !rows_in_regs;
+        bool deep = false;
         long long tk0 = 0;
         if (PROF) tk0 = clock64();
         // =============================================================== fast vote
@@ -182,15 +181,13 @@ k_consensus(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, const PairD
         // lane decodes its entry, the dominant link "match after match" (col 0, pd 0, pb = seed
         // base) is counted with one ballot per chunk, everything else goes through shared-memory
         // atomics; coverage / max_delta / deep are reduced once at the end.
-        if (rows_in_regs) {
+        {
             const int idx_maj = 1 + Sp;
             int cov_lane = 0, nins_lane = 0, maj_cnt = 0, maj_first = NOFIRST; bool deep_lane = false;
-#pragma unroll
-            for (int c = 0; c < NCHR; c++) {
-                if (c * 32 >= RB) continue;
-                const uint32_t ec = ecv[c], ep = epv[c];
+            // one chunk of 32 pairs: decode the entry of this lane's pair and vote
+            auto vote_chunk = [&](const uint32_t ec, const uint32_t ep, const int cbase) {
                 const bool act = (ec & ENT_VALID) != 0;
-                const int ai = c * 32 + lane;
+                const int ai = cbase + lane;
                 const int m = (ec & ENT_MATCH) ? 1 : 0;
                 const int nins = act ? ent_nins(ec) : 0;
                 const int b0 = m ? Si : 4;
@@ -208,7 +205,7 @@ k_consensus(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, const PairD
                 const bool vote = act && !dpl;
                 const unsigned majb = __ballot_sync(FULL, vote && idx0 == idx_maj);
                 maj_cnt += __popc(majb);
-                if (majb && maj_first == NOFIRST) maj_first = c * 32 + __ffs(majb) - 1;
+                if (majb && maj_first == NOFIRST) maj_first = cbase + __ffs(majb) - 1;
                 if (vote && idx0 != idx_maj) { atomicAdd(&sm.cnt[idx0], 1); atomicMin(&sm.first[idx0], ai); }
                 if (vote && nins >= 1) {                       // insertion tags (few lanes: divergent is fine)
                     int pb = b0;
@@ -219,6 +216,16 @@ k_consensus(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, const PairD
                         pb = bb;
                     }
                 }
+            };
+#pragma unroll
+            for (int c = 0; c < NCHR; c++) {
+                if (c * 32 >= RB) continue;
+                vote_chunk(ecv[c], epv[c], c * 32);
+            }
+            // blocks with more than NCHR*32 pairs: the remaining chunks straight from the matrix
+            for (int c0 = NCHR * 32; c0 < RB; c0 += 32) {
+                const uint32_t* row = Mb + (size_t)i * RB + c0 + lane;
+                vote_chunk(__ldg(row), i > 0 ? __ldg(row - RB) : 0u, c0);
             }
             if (lane == 0 && maj_cnt) { sm.cnt[idx_maj] = maj_cnt; sm.first[idx_maj] = maj_first; }
             deep = __ballot_sync(FULL, deep_lane) != 0;

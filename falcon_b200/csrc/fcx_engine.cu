@@ -113,6 +113,7 @@ struct fcx_ctx {
     uint32_t max_wave_pairs = 1u << 19;
     uint32_t min_wave_blocks = 384;
     int n_lanes = 2;
+    int active_lanes = 0;              // 0 = all
 };
 
 static thread_local std::string g_create_err;
@@ -204,6 +205,7 @@ extern "C" int fcx_set_option(fcx_ctx* ctx, const char* name, double value) {
     else if (n == "arena_gb") ctx->arena_budget = (size_t)(value * (double)((size_t)1 << 30));
     else if (n == "max_wave_blocks") ctx->max_wave_blocks = (uint32_t)value;
     else if (n == "min_wave_blocks") ctx->min_wave_blocks = (uint32_t)value;
+    else if (n == "lanes") ctx->active_lanes = value <= 0 ? 0 : std::min((int)value, (int)ctx->lanes.size());
     else { ctx->err = "unknown option: " + n; return 1; }
     return 0;
 }
@@ -488,7 +490,7 @@ extern "C" int fcx_consensus_blocks(fcx_ctx* ctx, uint32_t n_blocks, const uint3
     // ---- plan waves from upper bounds (exact sizes are computed per wave after k_range).
     // Aim for >= 2 waves per lane so that stages of different waves overlap, but keep waves large
     // enough (min_wave_blocks) for the one-warp-per-block consensus kernel to fill the GPU.
-    const int nl = (int)ctx->lanes.size();
+    const int nl = ctx->active_lanes > 0 ? ctx->active_lanes : (int)ctx->lanes.size();
     const int wpl = getenv("FCX_WAVES_PER_LANE") ? std::max(1, atoi(getenv("FCX_WAVES_PER_LANE"))) : 1;
     uint32_t target = (n_blocks + wpl * nl - 1) / (wpl * nl);
     target = std::max(target, ctx->min_wave_blocks);

@@ -160,7 +160,9 @@ enum { FCX_C_PAIRS = 0, FCX_C_DP_PAIRS, FCX_C_ACCEPTED, FCX_C_TRACE_CELLS, FCX_C
 int fcx_last_stats(fcx_ctx *, double *times_ms /*FCX_T_COUNT*/, uint64_t *counters /*FCX_C_COUNT*/);
 
 /* Engine options: "pair_info" (0/1, keep per-pair diagnostics; default 1), "arena_gb" (device
- * memory budget for wave buffers), "max_wave_blocks", "min_wave_blocks", "profile" (0/1). */
+ * memory budget for wave buffers), "max_wave_blocks", "min_wave_blocks", "lanes" (waves in flight,
+ * 1..FCX_LANES; with 1 the per-kernel timings of fcx_last_stats are not inflated by overlap),
+ * "profile" (0/1). */
 int fcx_set_option(fcx_ctx *, const char *name, double value);
 
 /* CUDA-event stopwatch on the engine's stream: start records an event, stop records a second one,

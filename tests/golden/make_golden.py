@@ -73,6 +73,8 @@ def main():
     cases["synth8_default"] = (txt, ["--n-core", "0", "--min-cov", "4", "--min-n-read", "5"])
     cases["synth8_full_maxn12"] = (txt, ["--n-core", "0", "--output-full", "--min-cov", "2", "--max-n-read", "12",
                                          "--min-cov-aln", "2"])
+    cases["synth8_trim_multi"] = (txt, ["--n-core", "0", "--trim", "--output-multi", "--min-cov", "3", "--trim-size", "30",
+                                         "--edge-tolerance", "800"])
     S2 = synth.make_set(25000, 2500, 20, seed=11, n_blocks=6, len_sigma=0.5)
     txt2 = S2.la4falcon_text() .replace(b"- -\n", b"junk line with three tokens\n* *\n- -\n")
     cases["synth6_ragged_multi"] = (txt2, ["--n-core", "0", "--output-multi", "--min-cov", "3", "--min-len-aln", "1500",

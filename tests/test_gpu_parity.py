@@ -220,3 +220,23 @@ def test_legacy_align_symbol(oracle):
             assert (got["dist"], got["qe"], got["te"]) == (o["dist"], o["q_e"], o["t_e"])
             if want_str:
                 assert got["qa"] == o["q_aln"] and got["ta"] == o["t_aln"]
+
+
+@pytest.mark.parametrize("read_len,genome", [(30000, 150000), (60000, 240000)])
+def test_long_reads_vs_oracle(engine, oracle, read_len, genome):
+    """BASELINE config 4 (read-length sweep): 30 kb and 60 kb reads, one block each, bit-exact."""
+    S = synth.make_set(genome, read_len, 12, seed=31, n_blocks=1, block_stride=3)
+    engine.upload_pool(S.pool)
+    got = engine.consensus_blocks([b.tolist() for b in S.blocks], 2, 0.70)
+    for bi in range(len(S.blocks)):
+        assert got[bi] == oracle.generate_consensus(S.block_seqs(bi), 2, 0.70)
+
+
+def test_block_with_more_than_256_pairs(engine, oracle):
+    """--max-n-read defaults to 500 (consensus.py:233): rows beyond the 8 register-resident chunks
+    of the consensus kernel are read straight from the pile-up matrix."""
+    S = synth.make_set(30000, 2000, 330, seed=41, n_blocks=1, block_stride=250, max_n_read=500, min_ovl=200)
+    assert len(S.blocks[0]) > 300
+    engine.upload_pool(S.pool)
+    got = engine.consensus_blocks([S.blocks[0].tolist()], 6, 0.70)[0]
+    assert got == oracle.generate_consensus(S.block_seqs(0), 6, 0.70)
