@@ -33,6 +33,7 @@ struct CnsOut { int32_t len; int32_t err; int32_t deep_positions; int32_t positi
                 long long cyc_vote, cyc_dp, cyc_generic, cyc_backtrack; };
 
 constexpr int CNS_WARPS = 4;
+constexpr int CNS_CTAS_PER_SM = 5;   // 20 resident warps / SM: caps registers at 102 per thread
 constexpr int LINK_CAP = 512;     // generic path: distinct (delta, base, link) entries per position
 constexpr int LVL = 255 * 5;      // (delta, base) slots of one position
 constexpr int RCAP = 160;         // accepted reads whose metadata is cached in shared memory
@@ -73,7 +74,7 @@ struct LvlTab {      // score / record tables of one position: first 8 levels in
 };
 
 template <bool PROF>
-__global__ void __launch_bounds__(CNS_WARPS * 32)
+__global__ void __launch_bounds__(CNS_WARPS * 32, CNS_CTAS_PER_SM)
 k_consensus(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, const PairDesc* __restrict__ pairs,
             const PairRange* __restrict__ ranges, const PairAlloc* __restrict__ allocs,
             const PairAln* __restrict__ aln, const uint32_t* __restrict__ pool,
@@ -107,7 +108,7 @@ k_consensus(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, const PairD
         if (j < bd.n_pairs) {
             const uint32_t p = bd.pair_begin + j;
             const PairAln a = aln[p];
-            ok = a.accepted != 0;
+            ok = a.accepted > 0;
             if (ok) {
                 const PairRange rg = ranges[p];
                 const uint64_t xo = allocs[p].xam_off;

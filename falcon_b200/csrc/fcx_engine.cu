@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <thread>
 #include <vector>
@@ -109,11 +110,12 @@ struct fcx_ctx {
     double prof[8] = {0};
     cudaEvent_t tev[2] = {nullptr, nullptr};
     size_t arena_budget = (size_t)120 << 30;
-    uint32_t max_wave_blocks = 2368;     // 148 SMs x 16 resident consensus warps
+    uint32_t max_wave_blocks = 2960;     // 148 SMs x 20 resident consensus warps (set from the SM count)
     uint32_t max_wave_pairs = 1u << 19;
     uint32_t min_wave_blocks = 384;
     int n_lanes = 2;
     int active_lanes = 0;              // 0 = all
+    uint32_t debug_split_above = 0;    // test hook: pretend waves with more blocks than this do not fit
 };
 
 static thread_local std::string g_create_err;
@@ -131,6 +133,20 @@ static thread_local std::string g_create_err;
     } while (0)
 #define CK(call) CKE(ctx->err, call)
 #define CKL(call) CKE(L.err, call)
+// buffer growth inside a wave: an out-of-memory condition is reported as 100 so that the caller
+// can split the wave instead of failing
+#define CKR(call)                                                                         \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ == cudaErrorMemoryAllocation) { cudaGetLastError(); L.err = "out of device memory"; return 100; } \
+        if (e_ != cudaSuccess) {                                                          \
+            char buf_[512];                                                               \
+            snprintf(buf_, sizeof buf_, "%s failed: %s (%s:%d)", #call,                   \
+                     cudaGetErrorString(e_), __FILE__, __LINE__);                         \
+            L.err = buf_;                                                                 \
+            return 1;                                                                     \
+        }                                                                                 \
+    } while (0)
 
 extern "C" const char* fcx_version(void) { return "falcon_b200 0.2 sm_100a"; }
 
@@ -161,6 +177,12 @@ extern "C" int fcx_create(int device, fcx_ctx** out) {
     if (const char* s = getenv("FCX_LANES")) ctx->n_lanes = std::max(1, atoi(s));
     if (const char* s = getenv("FCX_PROFILE")) ctx->profile = atoi(s) != 0;
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (!getenv("FCX_WAVE_BLOCKS")) ctx->max_wave_blocks = (uint32_t)(ctx->sm_count * CNS_CTAS_PER_SM * CNS_WARPS);
+    {   // never plan beyond what the device can actually give
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && !getenv("FCX_ARENA_GB"))
+            ctx->arena_budget = std::min(ctx->arena_budget, (size_t)((double)free_b * 0.70));
+    }
     cudaFuncSetAttribute(k_range, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          RANGE_WARPS * RANGE_BINS * (int)sizeof(int));
     ctx->lanes.resize(ctx->n_lanes);
@@ -205,6 +227,7 @@ extern "C" int fcx_set_option(fcx_ctx* ctx, const char* name, double value) {
     else if (n == "arena_gb") ctx->arena_budget = (size_t)(value * (double)((size_t)1 << 30));
     else if (n == "max_wave_blocks") ctx->max_wave_blocks = (uint32_t)value;
     else if (n == "min_wave_blocks") ctx->min_wave_blocks = (uint32_t)value;
+    else if (n == "debug_split_above") ctx->debug_split_above = (uint32_t)value;
     else if (n == "lanes") ctx->active_lanes = value <= 0 ? 0 : std::min((int)value, (int)ctx->lanes.size());
     else { ctx->err = "unknown option: " + n; return 1; }
     return 0;
@@ -264,6 +287,7 @@ inline uint64_t max_d_of(int q_len, int t_len) { return (uint64_t)(int)(0.3 * (q
 int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* block_off, const uint32_t* read_ids,
              unsigned min_cov, double min_idt, WaveResult& res) {
     const uint32_t nb = b1 - b0;
+    if (ctx->debug_split_above && nb > ctx->debug_split_above) { L.err = "out of device memory (simulated)"; return 100; }
     std::vector<BlockDesc> hb(nb);
     uint64_t npairs64 = 0, kpos_total = 0, rec_total = 0, cns_total = 0, m_total = 0, tiles = 0;
     uint32_t max_np = 1;
@@ -298,20 +322,20 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
     }
     cudaStream_t st = L.stream;
     const size_t np1 = std::max(np, 1u);
-    CKL(L.d_blocks.reserve(nb * sizeof(BlockDesc)));
-    CKL(L.d_pairs.reserve(np1 * sizeof(PairDesc)));
-    CKL(L.d_ranges.reserve(np1 * sizeof(PairRange)));
-    CKL(L.d_allocs.reserve(np1 * sizeof(PairAlloc)));
-    CKL(L.d_aln.reserve(np1 * sizeof(PairAln)));
-    CKL(L.d_ktab.reserve((size_t)nb * KTAB * 4));
-    CKL(L.d_kpos.reserve(kpos_total * 4 + 16));
-    CKL(L.d_recs.reserve(rec_total * sizeof(CnsRec)));
-    CKL(L.d_cns.reserve(cns_total));
-    CKL(L.d_eqv.reserve(cns_total * 4));
-    CKL(L.d_cnsout.reserve(nb * sizeof(CnsOut)));
+    CKR(L.d_blocks.reserve(nb * sizeof(BlockDesc)));
+    CKR(L.d_pairs.reserve(np1 * sizeof(PairDesc)));
+    CKR(L.d_ranges.reserve(np1 * sizeof(PairRange)));
+    CKR(L.d_allocs.reserve(np1 * sizeof(PairAlloc)));
+    CKR(L.d_aln.reserve(np1 * sizeof(PairAln)));
+    CKR(L.d_ktab.reserve((size_t)nb * KTAB * 4));
+    CKR(L.d_kpos.reserve(kpos_total * 4 + 16));
+    CKR(L.d_recs.reserve(rec_total * sizeof(CnsRec)));
+    CKR(L.d_cns.reserve(cns_total));
+    CKR(L.d_eqv.reserve(cns_total * 4));
+    CKR(L.d_cnsout.reserve(nb * sizeof(CnsOut)));
     const uint32_t cns_grid = (nb + CNS_WARPS - 1) / CNS_WARPS;
-    CKL(L.d_lvl.reserve((size_t)cns_grid * CNS_WARPS * 4 * LVL * 4));
-    CKL(L.d_meta.reserve((size_t)cns_grid * CNS_WARPS * max_np * sizeof(ReadMeta)));
+    CKR(L.d_lvl.reserve((size_t)cns_grid * CNS_WARPS * 4 * LVL * 4));
+    CKR(L.d_meta.reserve((size_t)cns_grid * CNS_WARPS * max_np * sizeof(ReadMeta)));
     CKL(L.h_ranges.reserve(np1 * sizeof(PairRange)));
     CKL(L.h_aln.reserve(np1 * sizeof(PairAln)));
     CKL(L.h_cns.reserve(cns_total));
@@ -331,7 +355,7 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
     // ---- range
     if (np) {
         const unsigned rgrid = std::min<unsigned>((np + RANGE_WARPS - 1) / RANGE_WARPS, (unsigned)ctx->sm_count * 3u);
-        CKL(L.d_rlist.reserve((size_t)rgrid * RANGE_WARPS * RANGE_LIST_CAP * sizeof(int2)));
+        CKR(L.d_rlist.reserve((size_t)rgrid * RANGE_WARPS * RANGE_LIST_CAP * sizeof(int2)));
         k_range<<<rgrid, RANGE_WARPS * 32, RANGE_WARPS * RANGE_BINS * sizeof(int), st>>>(
             L.d_blocks.as<BlockDesc>(), L.d_pairs.as<PairDesc>(), np, pool, L.d_ktab.as<uint32_t>(),
             L.d_kpos.as<uint32_t>(), L.d_rlist.as<int2>(), L.d_ranges.as<PairRange>());
@@ -346,19 +370,25 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
     uint64_t trace_recs = 0, xam_n = 0, path_w = 0, dp_pairs = 0, span_bases = 0;
     const PairRange* hr = L.h_ranges.as<PairRange>();
     for (uint32_t p = 0; p < np; p++) {
-        ha[p].trace_off = trace_recs; ha[p].xam_off = xam_n; ha[p].path_off = path_w;
+        ha[p].trace_off = trace_recs; ha[p].xam_off = xam_n; ha[p].path_off = path_w; ha[p].trace_cap = 0; ha[p].pad_ = 0;
         if (hr[p].pass) {
             int ql = hr[p].e1 - hr[p].s1, tl = hr[p].e2 - hr[p].s2;
+            // Only accepted pairs are traced back, and acceptance needs D / A < max_diff with
+            // A = (q_e + t_e + D) / 2 <= (q + t + D) / 2, i.e. D < max_diff (q + t) / (2 - max_diff):
+            // steps beyond that bound need no trace record.
+            const double mdiff = 1.0 - min_idt;
             uint64_t md = max_d_of(ql, tl);
+            if (mdiff < 1.999) md = std::min<uint64_t>(md, (uint64_t)(mdiff * (ql + tl) / (2.0 - mdiff)) + 2);
+            ha[p].trace_cap = (uint32_t)(md + 1); ha[p].pad_ = 0;
             trace_recs += md + 1; xam_n += (uint64_t)tl + 2; path_w += md / 32 + 2;
             dp_pairs++; span_bases += (uint64_t)ql + tl;
         }
     }
-    CKL(L.d_trace.reserve(trace_recs * TRACE_REC_WORDS * 4 + 64));
-    CKL(L.d_xam.reserve(xam_n * 4 + 128));
-    CKL(L.d_ent.reserve(xam_n * 4 + 128));
-    CKL(L.d_path.reserve(path_w * 4 + 64));
-    CKL(L.d_M.reserve(m_total * 4 + 64));
+    CKR(L.d_trace.reserve(trace_recs * TRACE_REC_WORDS * 4 + 64));
+    CKR(L.d_xam.reserve(xam_n * 4 + 128));
+    CKR(L.d_ent.reserve(xam_n * 4 + 128));
+    CKR(L.d_path.reserve(path_w * 4 + 64));
+    CKR(L.d_M.reserve(m_total * 4 + 64));
     if (np) CKL(cudaMemcpyAsync(L.d_allocs.p, ha.data(), (size_t)np * sizeof(PairAlloc), cudaMemcpyHostToDevice, st));
     // ---- DP
     CKL(cudaEventRecord(L.ev[3], st));
@@ -444,6 +474,7 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
     uint64_t cells = 0, steps = 0, cols = 0, accepted = 0;
     if (ctx->keep_pair_info) res.info.reserve(np);
     for (uint32_t p = 0; p < np; p++) {
+        if (hal[p].accepted < 0) { L.err = "internal error: accepted alignment beyond its trace bound"; return 4; }
         cells += (uint64_t)hal[p].cells; accepted += hal[p].accepted;
         if (hal[p].aligned) steps += (uint64_t)hal[p].dist + 1;
         if (hal[p].accepted) cols += (uint64_t)hal[p].aln_size;
@@ -502,10 +533,14 @@ extern "C" int fcx_consensus_blocks(fcx_ctx* ctx, uint32_t n_blocks, const uint3
         while (e < n_blocks) {
             uint32_t lo = block_off[e], hi = block_off[e + 1];
             int slen = ctx->h_len[read_ids[lo]];
+            const double mdiff = 1.0 - min_idt;
+            const double capfrac = std::min(0.3, mdiff < 1.999 ? mdiff / (2.0 - mdiff) : 0.3);
             double bb = (double)KTAB * 4 + (double)slen * (4 + 8 * 12 + 2 * 5) + 4.0 * slen * (((hi - lo - 1) + 31) & ~31u);
             for (uint32_t i = lo + 1; i < hi; i++) {
-                int rl = ctx->h_len[read_ids[i]];
-                bb += 0.3 * (std::min(rl, slen) * 2.0) * 36.0 + 8.0 * (std::min(rl, slen) + 2) + 128;
+                // typical aligned span ~ 0.65 x the shorter sequence (exact sizes follow k_range;
+                // an under-estimate is caught by the out-of-memory split below)
+                const double span = 0.65 * std::min(ctx->h_len[read_ids[i]], slen);
+                bb += capfrac * 2.0 * span * 33.0 + 8.0 * (span + 2) + 128;
             }
             if (e > b && (bytes + bb > budget || pairs + (hi - lo - 1) > ctx->max_wave_pairs || e - b >= target)) break;
             bytes += bb; pairs += hi - lo - 1; e++;
@@ -520,13 +555,30 @@ extern "C" int fcx_consensus_blocks(fcx_ctx* ctx, uint32_t n_blocks, const uint3
     std::vector<WaveResult> results(waves.size());
     std::atomic<size_t> next(0);
     std::atomic<int> failed(0);
+    // a wave that does not fit (code 100) is split in two and retried; results stay in block order
+    std::function<int(Lane&, uint32_t, uint32_t, WaveResult&)> run_split =
+        [&](Lane& L, uint32_t b0, uint32_t b1, WaveResult& out) -> int {
+        int rc = run_wave(ctx, L, b0, b1, block_off, read_ids, min_cov, min_idt, out);
+        if (rc != 100) return rc;
+        if (b1 - b0 <= 1) { L.err = "a single seed block does not fit in device memory"; return 1; }
+        out = WaveResult();
+        const uint32_t mid = b0 + (b1 - b0) / 2;
+        WaveResult a, b;
+        if ((rc = run_split(L, b0, mid, a))) return rc;
+        if ((rc = run_split(L, mid, b1, b))) return rc;
+        out.bases = std::move(a.bases); out.bases.insert(out.bases.end(), b.bases.begin(), b.bases.end());
+        out.lens = std::move(a.lens); out.lens.insert(out.lens.end(), b.lens.begin(), b.lens.end());
+        out.info = std::move(a.info); out.info.insert(out.info.end(), b.info.begin(), b.info.end());
+        out.eqv = std::move(a.eqv); out.eqv.insert(out.eqv.end(), b.eqv.begin(), b.eqv.end());
+        return 0;
+    };
     auto worker = [&](int li) {
         cudaSetDevice(ctx->device);
         Lane& L = ctx->lanes[li];
         for (;;) {
             size_t w = next.fetch_add(1);
             if (w >= waves.size() || failed.load()) break;
-            int rc = run_wave(ctx, L, waves[w].first, waves[w].second, block_off, read_ids, min_cov, min_idt, results[w]);
+            int rc = run_split(L, waves[w].first, waves[w].second, results[w]);
             if (rc) { failed.store(rc); break; }
         }
     };

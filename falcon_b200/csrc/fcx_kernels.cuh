@@ -59,6 +59,8 @@ struct PairAlloc {        // host-computed after k_range
     uint64_t trace_off;   // in 32-byte trace records
     uint64_t xam_off;     // in uint32 entries
     uint64_t path_off;    // in uint32 words
+    uint32_t trace_cap;   // trace records available: steps d >= trace_cap are not recorded (such a
+    uint32_t pad_;        // pair can no longer be accepted, see fcx_engine.cu)
 };
 
 struct PairAln {          // output of k_dp / k_traceback
@@ -436,7 +438,7 @@ k_range(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs
 // traceback kernel re-walks the path and recomputes the snakes.
 // Steps whose band holds <= 64 cells (virtually all) run a register-resident fast path with one
 // or two cells per lane; wider bands (<= 151 cells) take the generic chunk loop.
-constexpr int DP_WARPS = 8;
+constexpr int DP_WARPS = 4;
 constexpr int VRING = 512;
 
 __device__ __forceinline__ void snake(const uint32_t* __restrict__ q, const uint32_t* __restrict__ t,
@@ -509,7 +511,9 @@ k_dp(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs,
     asm volatile("" : "+r"(max_d));     // keep the FP64 conversion out of the d loop (ptxas rematerialises it)
     const int band_size = BAND_TOL * 2;                        // :151
     int* V = s_V[wib];
-    uint32_t* trace = trace_arena + allocs[p].trace_off * TRACE_REC_WORDS;
+    const PairAlloc al = allocs[p];
+    uint32_t* trace = trace_arena + al.trace_off * TRACE_REC_WORDS;
+    const int trace_cap = (int)al.trace_cap;
 
     int best_m = -1, min_k = 0, max_k = 0, cells = 0;
     bool aligned = false; int end_d = 0, end_k = 0, end_x = 0, end_y = 0;
@@ -545,7 +549,7 @@ k_dp(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs,
             }
             const unsigned up0 = __ballot_sync(FULL, c0.up);
             const unsigned up1 = two ? __ballot_sync(FULL, c1.up) : 0u;
-            if (lane == 0) {
+            if (lane == 0 && d < trace_cap) {
                 *reinterpret_cast<uint2*>(rec) = make_uint2((uint32_t)min_k, up0);
                 if (two) rec[2] = up1;
             }
@@ -575,7 +579,8 @@ k_dp(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs,
         }
         // ---------------------------------------------------- generic step: up to 151 cells
         const int nch = (ncell + 31) >> 5;
-        if (lane == 0) rec[0] = (uint32_t)min_k;
+        const bool rec_ok = d < trace_cap;
+        if (lane == 0 && rec_ok) rec[0] = (uint32_t)min_k;
         int step_best = best_m;
         for (int c = 0; c < nch; c++) {
             const int k = min_k + 2 * (lane + 32 * c);
@@ -583,7 +588,7 @@ k_dp(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs,
             DpCell cc; cc.x = cc.y = 0; cc.up = false;
             if (act) cc = dp_cell(V, d, k, min_k, max_k, q, t, qs, ts, q_len, t_len);
             unsigned upb = __ballot_sync(FULL, act && cc.up);
-            if (lane == 0) rec[1 + c] = upb;
+            if (lane == 0 && rec_ok) rec[1 + c] = upb;
             const bool fin = act && (cc.x >= q_len || cc.y >= t_len);
             unsigned finb = __ballot_sync(FULL, fin);
             if (act) V[k & (VRING - 1)] = cc.x;
@@ -621,6 +626,7 @@ k_dp(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs,
         res.aln_size = (end_x + end_y + end_d) / 2;            // :256, equals the traced length
         res.accepted = (res.aln_size > 500 &&
                         ((double)res.dist / (double)res.aln_size) < max_diff) ? 1 : 0;   // falcon.c:629
+        if (res.accepted && end_d >= trace_cap) res.accepted = -1;     // cannot happen (bound in fcx_engine.cu); loud if it does
     }
     res.cells = cells;
     if (lane == 0) out[p] = res;
@@ -653,7 +659,7 @@ __global__ void k_traceback(const BlockDesc* __restrict__ blocks, const PairDesc
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_pairs) return;
     PairAln a = aln[p];
-    if (!a.accepted) return;
+    if (a.accepted <= 0) return;
     const PairRange rg = ranges[p];
     const PairDesc pd = pairs[p];
     const uint32_t* q = pool + pd.read_woff;
@@ -890,7 +896,7 @@ k_transpose(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, uint32_t n_
         if (j < bd.n_pairs) {
             const uint32_t p = bd.pair_begin + j;
             const PairAln a = aln[p];
-            if (a.accepted) { my_ts = ranges[p].s2; my_cnt = a.t_cnt; my_off = allocs[p].xam_off; }
+            if (a.accepted > 0) { my_ts = ranges[p].s2; my_cnt = a.t_cnt; my_off = allocs[p].xam_off; }
         }
     }
     const int i = i0 + lane;

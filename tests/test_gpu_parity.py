@@ -240,3 +240,18 @@ def test_block_with_more_than_256_pairs(engine, oracle):
     engine.upload_pool(S.pool)
     got = engine.consensus_blocks([S.blocks[0].tolist()], 6, 0.70)[0]
     assert got == oracle.generate_consensus(S.block_seqs(0), 6, 0.70)
+
+
+def test_wave_split_on_out_of_memory(oracle):
+    """A wave that does not fit is split and retried (simulated with the engine's test hook); the
+    merged output must be unchanged."""
+    from falcon_b200.binding import Engine
+    S = synth.make_set(60000, 4000, 25, seed=12, n_blocks=9)
+    e = Engine(0)
+    e.upload_pool(S.pool)
+    blocks = [b.tolist() for b in S.blocks]
+    a = e.consensus_blocks(blocks, 4, 0.70)
+    e.set_option("debug_split_above", 2)
+    b = e.consensus_blocks(blocks, 4, 0.70)
+    assert a == b and e.stats()["waves"] >= 5
+    assert len(e.pair_info()) == S.n_pairs
