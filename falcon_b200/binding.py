@@ -109,6 +109,15 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
                                          C.POINTER(C.c_void_p)]
     lib.fcx_last_pair_info.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     lib.fcx_last_stats.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+    lib.fcx_parser_create.argtypes = [C.c_uint] * 5
+    lib.fcx_parser_create.restype = C.c_void_p
+    lib.fcx_parser_destroy.argtypes = [C.c_void_p]
+    lib.fcx_parser_feed.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_int]
+    lib.fcx_parser_pending.argtypes = [C.c_void_p]
+    lib.fcx_parser_stopped.argtypes = [C.c_void_p]
+    lib.fcx_parser_take.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                    C.POINTER(C.c_uint32), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                    C.POINTER(C.c_uint32), C.POINTER(C.c_void_p)]
     lib.fcx_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
     lib.fcx_timer_start.argtypes = [C.c_void_p]
     lib.fcx_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
@@ -254,3 +263,51 @@ class Engine:
         d = {"ms_" + k: t[i] for i, k in enumerate(T_NAMES)}
         d.update({k: int(c[i]) for i, k in enumerate(C_NAMES)})
         return d
+
+
+class StreamParser:
+    """LA4Falcon block-stream parser in the native library (fcx_parser_*), the C counterpart of
+    falcon_kit/mains/consensus.py:get_seq_data + get_longest_reads."""
+
+    def __init__(self, min_n_read: int, min_len_aln: int, max_n_read: int, min_cov_aln: int, max_cov_aln: int):
+        self._lib = lib()
+        self._h = self._lib.fcx_parser_create(min_n_read, min_len_aln, max_n_read, min_cov_aln, max_cov_aln)
+        self.stopped = False
+
+    def close(self):
+        if self._h:
+            self._lib.fcx_parser_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def feed(self, data: bytes, eof: bool = False) -> int:
+        rc = self._lib.fcx_parser_feed(self._h, data, len(data), 1 if eof else 0)
+        if rc < 0:
+            self.stopped = True
+            return -rc - 1
+        return rc
+
+    def pending(self) -> int:
+        return self._lib.fcx_parser_pending(self._h)
+
+    def take(self, max_blocks: int, max_bases: int):
+        """-> (bases_ptr, offsets (uint64 array), block_off, read_ids (uint32 arrays), seed ids)"""
+        b, o, bo, ri, si = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        nr, nb = C.c_uint32(), C.c_uint32()
+        self._lib.fcx_parser_take(self._h, max_blocks, max_bases, C.byref(b), C.byref(o), C.byref(nr), C.byref(bo),
+                                  C.byref(ri), C.byref(nb), C.byref(si))
+        n_reads, n_blocks = nr.value, nb.value
+        offsets = np.ctypeslib.as_array((C.c_uint64 * (n_reads + 1)).from_address(o.value)).copy()
+        block_off = np.ctypeslib.as_array((C.c_uint32 * (n_blocks + 1)).from_address(bo.value)).copy()
+        read_ids = np.ctypeslib.as_array((C.c_uint32 * max(1, int(block_off[-1]))).from_address(ri.value)).copy()[:int(block_off[-1])]
+        ids, addr = [], si.value
+        for _ in range(n_blocks):
+            sid = C.string_at(addr)
+            ids.append(sid.decode())
+            addr += len(sid) + 1
+        return b.value, offsets, block_off, read_ids, ids

@@ -197,6 +197,8 @@ def parse_args(argv):
     parser.add_argument("--device", type=int, default=None, help="CUDA device ordinal (default: $FCX_DEVICE or 0)")
     parser.add_argument("--batch-blocks", type=int, default=1024, help="seed blocks per GPU batch")
     parser.add_argument("--batch-bases", type=int, default=1 << 30, help="read bases per GPU batch")
+    parser.add_argument("--python-parser", action="store_true", default=False,
+                        help="parse stdin with the Python restatement of get_seq_data instead of the native parser")
     return parser.parse_args(_normalise_flags(argv[1:]))
 
 
@@ -259,6 +261,27 @@ def emit(out, cns: str, seed_id: str, args, good_region=re.compile("[ACGT]+")):
         out.write(runs[-1] + "\n")
 
 
+def run_native_parser(args, stdin, stdout, engine):
+    """stdin -> native parser (fcx_parser_*) -> engine, in batches; output in stdin order."""
+    from .binding import StreamParser
+    ps = StreamParser(args.min_n_read, args.min_len_aln, args.max_n_read, args.min_cov_aln, args.max_cov_aln)
+    done = False
+    while not done:
+        chunk = stdin.read(1 << 24)
+        eof = not chunk
+        pending = ps.feed(chunk or b"", eof)
+        done = eof or ps.stopped
+        while pending >= args.batch_blocks or (done and pending > 0):
+            bases_ptr, offsets, block_off, read_ids, ids = ps.take(args.batch_blocks, args.batch_bases)
+            engine.upload_pool_raw(bases_ptr, offsets)
+            data, off = engine.consensus_blocks_raw(block_off, read_ids, args.min_cov, args.min_idt, K)
+            raw = data.tobytes()
+            for i, sid in enumerate(ids):
+                emit(stdout, raw[int(off[i]):int(off[i + 1])].decode(), sid, args)
+            pending = ps.pending()
+    ps.close()
+
+
 def run(args, stdin=None, stdout=None, engine=None):
     logging.basicConfig(level=int(round(10 * args.verbose_level)))
     stdin = stdin if stdin is not None else sys.stdin.buffer
@@ -268,6 +291,10 @@ def run(args, stdin=None, stdout=None, engine=None):
         from .binding import Engine
         dev = args.device if args.device is not None else int(os.environ.get("FCX_DEVICE", "0"))
         engine = Engine(dev)
+    if not args.trim and not args.python_parser and hasattr(engine, "upload_pool_raw"):
+        run_native_parser(args, stdin, stdout, engine)
+        stdout.flush()
+        return
     config = (args.min_cov, K, args.max_n_read, args.min_idt, args.edge_tolerance, args.trim_size,
               args.min_cov_aln, args.max_cov_aln)
     runner = BatchRunner(engine, args.min_cov, args.min_idt, args.batch_blocks, args.batch_bases)

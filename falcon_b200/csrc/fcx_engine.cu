@@ -115,6 +115,7 @@ struct fcx_ctx {
     uint32_t min_wave_blocks = 384;
     int n_lanes = 2;
     int active_lanes = 0;              // 0 = all
+    bool dp_staged = false;            // TMA-staged k_dp variant (FCX_DP_STAGED=1 / option "dp_staged")
     uint32_t debug_split_above = 0;    // test hook: pretend waves with more blocks than this do not fit
 };
 
@@ -176,6 +177,8 @@ extern "C" int fcx_create(int device, fcx_ctx** out) {
     if (const char* s = getenv("FCX_WAVE_PAIRS")) ctx->max_wave_pairs = (uint32_t)atoi(s);
     if (const char* s = getenv("FCX_LANES")) ctx->n_lanes = std::max(1, atoi(s));
     if (const char* s = getenv("FCX_PROFILE")) ctx->profile = atoi(s) != 0;
+    if (const char* s = getenv("FCX_DP_STAGED")) ctx->dp_staged = atoi(s) != 0;
+    cudaFuncSetAttribute(k_dp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (!getenv("FCX_WAVE_BLOCKS")) ctx->max_wave_blocks = (uint32_t)(ctx->sm_count * CNS_CTAS_PER_SM * CNS_WARPS);
     {   // never plan beyond what the device can actually give
@@ -227,6 +230,7 @@ extern "C" int fcx_set_option(fcx_ctx* ctx, const char* name, double value) {
     else if (n == "arena_gb") ctx->arena_budget = (size_t)(value * (double)((size_t)1 << 30));
     else if (n == "max_wave_blocks") ctx->max_wave_blocks = (uint32_t)value;
     else if (n == "min_wave_blocks") ctx->min_wave_blocks = (uint32_t)value;
+    else if (n == "dp_staged") ctx->dp_staged = value != 0;
     else if (n == "debug_split_above") ctx->debug_split_above = (uint32_t)value;
     else if (n == "lanes") ctx->active_lanes = value <= 0 ? 0 : std::min((int)value, (int)ctx->lanes.size());
     else { ctx->err = "unknown option: " + n; return 1; }
@@ -367,7 +371,7 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
     CKL(cudaStreamSynchronize(st));
     // ---- exact per-pair allocations
     std::vector<PairAlloc> ha(np);
-    uint64_t trace_recs = 0, xam_n = 0, path_w = 0, dp_pairs = 0, span_bases = 0;
+    uint64_t trace_recs = 0, xam_n = 0, path_w = 0, dp_pairs = 0, span_bases = 0; uint32_t max_span = 0;
     const PairRange* hr = L.h_ranges.as<PairRange>();
     for (uint32_t p = 0; p < np; p++) {
         ha[p].trace_off = trace_recs; ha[p].xam_off = xam_n; ha[p].path_off = path_w; ha[p].trace_cap = 0; ha[p].pad_ = 0;
@@ -382,6 +386,7 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
             ha[p].trace_cap = (uint32_t)(md + 1); ha[p].pad_ = 0;
             trace_recs += md + 1; xam_n += (uint64_t)tl + 2; path_w += md / 32 + 2;
             dp_pairs++; span_bases += (uint64_t)ql + tl;
+            max_span = std::max(max_span, (uint32_t)std::max(ql, tl));
         }
     }
     CKR(L.d_trace.reserve(trace_recs * TRACE_REC_WORDS * 4 + 64));
@@ -393,9 +398,21 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
     // ---- DP
     CKL(cudaEventRecord(L.ev[3], st));
     if (np) {
-        k_dp<<<(np + DP_WARPS - 1) / DP_WARPS, DP_WARPS * 32, 0, st>>>(
-            L.d_blocks.as<BlockDesc>(), L.d_pairs.as<PairDesc>(), L.d_ranges.as<PairRange>(),
-            L.d_allocs.as<PairAlloc>(), np, pool, L.d_trace.as<uint32_t>(), 1.0 - min_idt, L.d_aln.as<PairAln>());
+        // staged variant: spans copied to shared memory by TMA when they fit the per-CTA budget
+        const int stage_words = (int)(((max_span + 15) / 16 + 1 + 8 + 3) & ~3u);
+        const size_t smem_staged = (size_t)DP_WARPS * ((size_t)VRING * 4 + (size_t)stage_words * 8 + 16);
+        const bool staged = ctx->dp_staged && smem_staged <= 100 * 1024;
+        if (staged) {
+            k_dp<true><<<(np + DP_WARPS - 1) / DP_WARPS, DP_WARPS * 32, smem_staged, st>>>(
+                L.d_blocks.as<BlockDesc>(), L.d_pairs.as<PairDesc>(), L.d_ranges.as<PairRange>(),
+                L.d_allocs.as<PairAlloc>(), np, pool, L.d_trace.as<uint32_t>(), 1.0 - min_idt, stage_words,
+                L.d_aln.as<PairAln>());
+        } else {
+            k_dp<false><<<(np + DP_WARPS - 1) / DP_WARPS, DP_WARPS * 32, (size_t)DP_WARPS * VRING * 4, st>>>(
+                L.d_blocks.as<BlockDesc>(), L.d_pairs.as<PairDesc>(), L.d_ranges.as<PairRange>(),
+                L.d_allocs.as<PairAlloc>(), np, pool, L.d_trace.as<uint32_t>(), 1.0 - min_idt, 0,
+                L.d_aln.as<PairAln>());
+        }
         CKL(cudaGetLastError());
         L.counters[FCX_C_KERNEL_LAUNCHES] += 1;
     }

@@ -77,6 +77,12 @@ __device__ __forceinline__ uint32_t fetch16(const uint32_t* __restrict__ w, int 
     uint32_t lo = __ldg(w + wi), hi = __ldg(w + wi + 1);
     return __funnelshift_r(lo, hi, (pos & 15) << 1);
 }
+// same, with the packed words staged in shared memory (k_dp<true>)
+template <bool SM>
+__device__ __forceinline__ uint32_t fetch16_t(const uint32_t* __restrict__ w, int pos) {
+    if (SM) { const int wi = pos >> 4; return __funnelshift_r(w[wi], w[wi + 1], (pos & 15) << 1); }
+    return fetch16(w, pos);
+}
 __device__ __forceinline__ int base_at(const uint32_t* __restrict__ w, int pos) {
     return (int)((__ldg(w + (pos >> 4)) >> ((pos & 15) << 1)) & 3u);
 }
@@ -441,12 +447,13 @@ k_range(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs
 constexpr int DP_WARPS = 4;
 constexpr int VRING = 512;
 
+template <bool SM = false>
 __device__ __forceinline__ void snake(const uint32_t* __restrict__ q, const uint32_t* __restrict__ t,
                                       int qs, int ts, int q_len, int t_len, int& x, int& y) {
     for (;;) {
         int rem = min(q_len - x, t_len - y);
         if (rem <= 0) break;
-        uint32_t diff = fetch16(q, qs + x) ^ fetch16(t, ts + y);
+        uint32_t diff = fetch16_t<SM>(q, qs + x) ^ fetch16_t<SM>(t, ts + y);
         int n = diff ? (__ffs(diff) - 1) >> 1 : 16;
         n = min(n, rem);
         x += n; y += n;
@@ -469,10 +476,11 @@ __device__ __forceinline__ DpCell dp_pick(const int* V, int k, int min_k, int ma
 
 // one 16-base compare (DW_banded.c:203-206), straight-line so that all lanes stay converged;
 // returns the advance (16 = all compared bases matched and neither end was reached: go on)
+template <bool SM = false>
 __device__ __forceinline__ int snake16(const uint32_t* __restrict__ q, const uint32_t* __restrict__ t,
                                        int qs, int ts, int q_len, int t_len, bool act, int& x, int& y) {
     const int rem = act ? max(min(q_len - x, t_len - y), 0) : 0;
-    const uint32_t diff = fetch16(q, qs + x) ^ fetch16(t, ts + y);
+    const uint32_t diff = fetch16_t<SM>(q, qs + x) ^ fetch16_t<SM>(t, ts + y);
     int n = diff ? (__ffs(diff) - 1) >> 1 : 16;
     n = min(n, rem);
     x += n; y += n;
@@ -480,25 +488,55 @@ __device__ __forceinline__ int snake16(const uint32_t* __restrict__ q, const uin
 }
 
 // full DP cell for the generic (wide band) path
+template <bool SM = false>
 __device__ __forceinline__ DpCell dp_cell(const int* V, int d, int k, int min_k, int max_k,
                                           const uint32_t* __restrict__ q, const uint32_t* __restrict__ t,
                                           int qs, int ts, int q_len, int t_len) {
     DpCell c;
     if (d == 0) { c.up = true; c.x = 0; c.y = -k; }        // V[k+1] is calloc'd 0
     else c = dp_pick(V, k, min_k, max_k, true);
-    snake(q, t, qs, ts, q_len, t_len, c.x, c.y);
+    snake<SM>(q, t, qs, ts, q_len, t_len, c.x, c.y);
     return c;
 }
 
+// TMA (1-D bulk async copy, cp.async.bulk -> SASS UBLKCP) + mbarrier helpers for the staged variant
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // init visible to the async (TMA) proxy
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(bytes),
+                    "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+    uint32_t ok = 0;
+    const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
+    while (!ok) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(b), "r"(phase) : "memory");
+    }
+}
+
+// STAGED = true: the two packed spans of the pair are copied into shared memory by one TMA bulk
+// copy each (dynamic shared memory: per warp V ring + 2 x stage_words words + an mbarrier) and the
+// snakes read shared memory; STAGED = false reads them through the read-only L1 path.
+template <bool STAGED>
 __global__ void __launch_bounds__(DP_WARPS * 32)
 k_dp(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs,
      const PairRange* __restrict__ ranges, const PairAlloc* __restrict__ allocs, uint32_t n_pairs,
      const uint32_t* __restrict__ pool, uint32_t* __restrict__ trace_arena, double max_diff,
-     PairAln* __restrict__ out) {
-    __shared__ int s_V[DP_WARPS][VRING];
+     int stage_words, PairAln* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char s_dyn[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t p = blockIdx.x * DP_WARPS + wib;
     if (p >= n_pairs) return;
+    const size_t per_warp = (size_t)VRING * 4 + (STAGED ? (size_t)stage_words * 8 + 16 : 0);
+    unsigned char* mine = s_dyn + (size_t)wib * per_warp;
+    int* V = reinterpret_cast<int*>(mine);
     PairAln res; res.aligned = res.dist = res.aln_size = res.q_e = res.t_e = res.k_end = 0;
     res.accepted = res.t_cnt = res.n_tags = res.cells = 0;
     const PairRange rg = ranges[p];
@@ -507,10 +545,26 @@ k_dp(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs,
     const uint32_t* q = pool + pd.read_woff;
     const uint32_t* t = pool + blocks[pd.block].seed_woff;
     const int qs = rg.s1, ts = rg.s2, q_len = rg.e1 - rg.s1, t_len = rg.e2 - rg.s2;
+    if (STAGED) {
+        uint32_t* sq = reinterpret_cast<uint32_t*>(mine + VRING * 4);
+        uint32_t* st = sq + stage_words;
+        uint64_t* bar = reinterpret_cast<uint64_t*>(st + stage_words);
+        // word windows, 16-byte aligned at both ends (+1 word: fetch16 reads one word ahead)
+        const int wq0 = (qs >> 4) & ~3, wq1 = (((qs + q_len + 15) >> 4) + 1 + 3) & ~3;
+        const int wt0 = (ts >> 4) & ~3, wt1 = (((ts + t_len + 15) >> 4) + 1 + 3) & ~3;
+        if (lane == 0) {
+            mbar_init(bar, 1);
+            mbar_expect_tx(bar, (uint32_t)((wq1 - wq0) + (wt1 - wt0)) * 4u);
+            tma_load_1d(sq, q + wq0, (uint32_t)(wq1 - wq0) * 4u, bar);
+            tma_load_1d(st, t + wt0, (uint32_t)(wt1 - wt0) * 4u, bar);
+        }
+        __syncwarp();
+        mbar_wait(bar, 0);
+        q = sq - wq0; t = st - wt0;
+    }
     int max_d = (int)(0.3 * (q_len + t_len));                 // DW_banded.c:149
     asm volatile("" : "+r"(max_d));     // keep the FP64 conversion out of the d loop (ptxas rematerialises it)
     const int band_size = BAND_TOL * 2;                        // :151
-    int* V = s_V[wib];
     const PairAlloc al = allocs[p];
     uint32_t* trace = trace_arena + al.trace_off * TRACE_REC_WORDS;
     const int trace_cap = (int)al.trace_cap;
@@ -520,7 +574,7 @@ k_dp(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs,
     // ---- d = 0 peeled: the single cell k = 0 starts at (0,0) (V is calloc'd, DW_banded.c:153,190-192)
     if (max_d > 0) {
         int x = 0, y = 0;
-        snake(q, t, qs, ts, q_len, t_len, x, y);               // same on every lane
+        snake<STAGED>(q, t, qs, ts, q_len, t_len, x, y);               // same on every lane
         if (lane == 0) { trace[0] = 0u; trace[1] = 1u; }
         cells = 1;
         if (x >= q_len || y >= t_len) { aligned = true; end_x = x; end_y = y; }
@@ -538,14 +592,14 @@ k_dp(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs,
             const bool a0 = k0 <= max_k, a1 = two && k1 <= max_k;
             DpCell c0 = dp_pick(V, k0, min_k, max_k, a0), c1;
             c1.x = c1.y = 0; c1.up = false;
-            int n0 = snake16(q, t, qs, ts, q_len, t_len, a0, c0.x, c0.y), n1 = 0;
+            int n0 = snake16<STAGED>(q, t, qs, ts, q_len, t_len, a0, c0.x, c0.y), n1 = 0;
             if (two) {
                 c1 = dp_pick(V, k1, min_k, max_k, a1);
-                n1 = snake16(q, t, qs, ts, q_len, t_len, a1, c1.x, c1.y);
+                n1 = snake16<STAGED>(q, t, qs, ts, q_len, t_len, a1, c1.x, c1.y);
             }
             while (__ballot_sync(FULL, n0 == 16 || n1 == 16)) {      // long snakes: rare
-                if (n0 == 16) n0 = snake16(q, t, qs, ts, q_len, t_len, true, c0.x, c0.y);
-                if (n1 == 16) n1 = snake16(q, t, qs, ts, q_len, t_len, true, c1.x, c1.y);
+                if (n0 == 16) n0 = snake16<STAGED>(q, t, qs, ts, q_len, t_len, true, c0.x, c0.y);
+                if (n1 == 16) n1 = snake16<STAGED>(q, t, qs, ts, q_len, t_len, true, c1.x, c1.y);
             }
             const unsigned up0 = __ballot_sync(FULL, c0.up);
             const unsigned up1 = two ? __ballot_sync(FULL, c1.up) : 0u;
@@ -586,7 +640,7 @@ k_dp(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs,
             const int k = min_k + 2 * (lane + 32 * c);
             const bool act = k <= max_k;
             DpCell cc; cc.x = cc.y = 0; cc.up = false;
-            if (act) cc = dp_cell(V, d, k, min_k, max_k, q, t, qs, ts, q_len, t_len);
+            if (act) cc = dp_cell<STAGED>(V, d, k, min_k, max_k, q, t, qs, ts, q_len, t_len);
             unsigned upb = __ballot_sync(FULL, act && cc.up);
             if (lane == 0 && rec_ok) rec[1 + c] = upb;
             const bool fin = act && (cc.x >= q_len || cc.y >= t_len);

@@ -1,0 +1,160 @@
+// fcx_parser.cu -- host-side parser of the LA4Falcon block stream.
+//
+// Restates, in C++, what falcon_kit/mains/consensus.py does per line in Python:
+//   get_seq_data      consensus.py:161-209  (2-token lines only; sequences > 100000 cut to 99999; the
+//                     first read of a block is the seed and is appended twice; duplicate ids are
+//                     dropped; "+" emits the block if len(seqs) >= min_n_read and
+//                     read_cov // seed_len >= min_cov_aln; "*" discards; "-" stops)
+//   get_longest_reads consensus.py:26-45    (seed + stable sort of the rest by -len, capped at
+//                     max_n_read / by max_cov_aln)
+// and hands the blocks out in the shape fcx_pool_upload / fcx_consensus_blocks take.  Pure host
+// code (text handling); no arithmetic of the hot path lives here.
+#include "../../include/falcon_b200.h"
+
+#include <algorithm>
+#include <cstring>
+#include <deque>
+#include <string>
+#include <unordered_set>
+#include <vector>
+
+namespace {
+
+struct Block {
+    std::string seed_id;
+    std::vector<std::string> seqs;     // [0] = seed, after get_longest_reads
+};
+
+inline bool is_space(unsigned char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\v' || c == '\f'; }
+
+}  // namespace
+
+struct fcx_parser {
+    unsigned min_n_read, min_len_aln, max_n_read, min_cov_aln, max_cov_aln;
+    std::string carry;                 // partial last line of the previous chunk
+    bool stopped = false;
+    // block under construction
+    std::vector<std::string> seqs;
+    std::string seed_id;
+    size_t seed_len = 0;
+    unsigned long long read_cov = 0;
+    std::unordered_set<std::string> ids;
+    std::deque<Block> ready;
+    // storage handed out by fcx_parser_take
+    std::vector<char> o_bases, o_ids;
+    std::vector<uint64_t> o_off;
+    std::vector<uint32_t> o_boff, o_rids;
+
+    void reset_block() { seqs.clear(); ids.clear(); seed_id.clear(); read_cov = 0; }
+
+    void emit_block() {
+        if (seqs.empty()) return;      // reference: ZeroDivisionError territory (read_cov // 0); skipped here
+        if (!(seqs.size() >= min_n_read && read_cov / seed_len >= min_cov_aln)) return;
+        // get_longest_reads(sort=True)
+        std::stable_sort(seqs.begin() + 1, seqs.end(),
+                         [](const std::string& a, const std::string& b) { return a.size() > b.size(); });
+        size_t keep = max_n_read;
+        if (max_cov_aln > 0) {
+            keep = 1; unsigned long long cov = 0;
+            for (size_t i = 1; i < seqs.size(); i++) {
+                if (cov / seed_len > max_cov_aln) break;
+                keep++; cov += seqs[i].size();
+            }
+            keep = std::min<size_t>(keep, max_n_read);
+        }
+        if (seqs.size() > keep) seqs.resize(keep);
+        Block b; b.seed_id = seed_id; b.seqs = std::move(seqs);
+        ready.push_back(std::move(b));
+        seqs.clear();
+    }
+
+    void line(const char* p, size_t n) {
+        if (stopped) return;
+        // l.strip().split(): tokens separated by ASCII whitespace; exactly two are required
+        size_t i = 0;
+        const char* tok[2]; size_t len[2]; int nt = 0;
+        while (i < n) {
+            while (i < n && is_space((unsigned char)p[i])) i++;
+            if (i >= n) break;
+            size_t s = i;
+            while (i < n && !is_space((unsigned char)p[i])) i++;
+            if (nt < 2) { tok[nt] = p + s; len[nt] = i - s; }
+            nt++;
+            if (nt > 2) return;
+        }
+        if (nt != 2) return;
+        size_t slen = len[1];
+        if (slen > 100000) slen = 99999;                                  // consensus.py:178-179
+        const bool ctrl = len[0] == 1 && (tok[0][0] == '+' || tok[0][0] == '-' || tok[0][0] == '*');
+        if (!ctrl) {
+            if (slen >= min_len_aln) {
+                std::string id(tok[0], len[0]);
+                if (seqs.empty()) { seqs.emplace_back(tok[1], slen); seed_len = slen; seed_id = id; }   // the seed
+                if (ids.insert(id).second) { seqs.emplace_back(tok[1], slen); read_cov += slen; }       // seed again, by design
+            }
+        } else if (tok[0][0] == '+') { emit_block(); reset_block(); }
+        else if (tok[0][0] == '*') { reset_block(); }
+        else { stopped = true; }
+    }
+};
+
+extern "C" fcx_parser* fcx_parser_create(unsigned min_n_read, unsigned min_len_aln, unsigned max_n_read,
+                                         unsigned min_cov_aln, unsigned max_cov_aln) {
+    fcx_parser* p = new fcx_parser();
+    p->min_n_read = min_n_read; p->min_len_aln = min_len_aln; p->max_n_read = max_n_read;
+    p->min_cov_aln = min_cov_aln; p->max_cov_aln = max_cov_aln;
+    return p;
+}
+extern "C" void fcx_parser_destroy(fcx_parser* p) { delete p; }
+
+extern "C" int fcx_parser_feed(fcx_parser* ps, const char* data, size_t n, int eof) {
+    size_t start = 0;
+    if (!ps->carry.empty()) {
+        const char* nl = (const char*)memchr(data, '\n', n);
+        if (!nl) { ps->carry.append(data, n); start = n; }
+        else {
+            ps->carry.append(data, (size_t)(nl - data));
+            ps->line(ps->carry.data(), ps->carry.size());
+            ps->carry.clear();
+            start = (size_t)(nl - data) + 1;
+        }
+    }
+    while (start < n && !ps->stopped) {
+        const char* nl = (const char*)memchr(data + start, '\n', n - start);
+        if (!nl) { ps->carry.assign(data + start, n - start); start = n; break; }
+        ps->line(data + start, (size_t)(nl - (data + start)));
+        start = (size_t)(nl - data) + 1;
+    }
+    if (eof && !ps->carry.empty()) { ps->line(ps->carry.data(), ps->carry.size()); ps->carry.clear(); }
+    return ps->stopped ? -(int)ps->ready.size() - 1 : (int)ps->ready.size();
+}
+
+extern "C" int fcx_parser_pending(const fcx_parser* ps) { return (int)ps->ready.size(); }
+extern "C" int fcx_parser_stopped(const fcx_parser* ps) { return ps->stopped ? 1 : 0; }
+
+extern "C" int fcx_parser_take(fcx_parser* ps, uint32_t max_blocks, uint64_t max_bases, const char** bases,
+                               const uint64_t** offsets, uint32_t* n_reads, const uint32_t** block_off,
+                               const uint32_t** read_ids, uint32_t* n_blocks, const char** seed_ids) {
+    ps->o_bases.clear(); ps->o_ids.clear(); ps->o_off.assign(1, 0); ps->o_boff.assign(1, 0); ps->o_rids.clear();
+    uint32_t nb = 0; uint64_t total = 0;
+    while (!ps->ready.empty() && nb < max_blocks) {
+        Block& b = ps->ready.front();
+        uint64_t sz = 0;
+        for (auto& s : b.seqs) sz += s.size();
+        if (nb > 0 && total + sz > max_bases) break;
+        for (auto& s : b.seqs) {
+            ps->o_rids.push_back((uint32_t)(ps->o_off.size() - 1));
+            ps->o_bases.insert(ps->o_bases.end(), s.begin(), s.end());
+            ps->o_off.push_back(ps->o_bases.size());
+        }
+        ps->o_boff.push_back((uint32_t)ps->o_rids.size());
+        ps->o_ids.insert(ps->o_ids.end(), b.seed_id.begin(), b.seed_id.end());
+        ps->o_ids.push_back('\0');
+        total += sz; nb++;
+        ps->ready.pop_front();
+    }
+    ps->o_bases.push_back('\0');
+    *bases = ps->o_bases.data(); *offsets = ps->o_off.data(); *n_reads = (uint32_t)(ps->o_off.size() - 1);
+    *block_off = ps->o_boff.data(); *read_ids = ps->o_rids.data(); *n_blocks = nb; *seed_ids = ps->o_ids.data();
+    return 0;
+}

@@ -159,6 +159,25 @@ enum { FCX_C_PAIRS = 0, FCX_C_DP_PAIRS, FCX_C_ACCEPTED, FCX_C_TRACE_CELLS, FCX_C
        FCX_C_ALN_COLS, FCX_C_SPAN_BASES, FCX_C_KERNEL_LAUNCHES, FCX_C_WAVES, FCX_C_COUNT };
 int fcx_last_stats(fcx_ctx *, double *times_ms /*FCX_T_COUNT*/, uint64_t *counters /*FCX_C_COUNT*/);
 
+/* ---------------------------------------------------------------- LA4Falcon stream parser
+ * Host-side parser of the stdin block text (replaces the per-line Python of
+ * falcon_kit/mains/consensus.py:161-209 and get_longest_reads :26-45; same rules, see
+ * fcx_parser.cu).  feed() takes arbitrary chunks of the stream and returns the number of complete
+ * blocks queued, or -(queued + 1) once the "- -" terminator has been seen; take() hands out up to
+ * max_blocks blocks (and at most max_bases bases, but at least one block) as a pool + block lists
+ * in exactly the shape fcx_pool_upload / fcx_consensus_blocks accept; seed_ids are NUL-separated.
+ * The returned buffers are owned by the parser and valid until the next take(). */
+typedef struct fcx_parser fcx_parser;
+fcx_parser *fcx_parser_create(unsigned min_n_read, unsigned min_len_aln, unsigned max_n_read,
+                              unsigned min_cov_aln, unsigned max_cov_aln);
+void fcx_parser_destroy(fcx_parser *);
+int fcx_parser_feed(fcx_parser *, const char *data, size_t n, int eof);
+int fcx_parser_pending(const fcx_parser *);
+int fcx_parser_stopped(const fcx_parser *);
+int fcx_parser_take(fcx_parser *, uint32_t max_blocks, uint64_t max_bases, const char **bases,
+                    const uint64_t **offsets, uint32_t *n_reads, const uint32_t **block_off,
+                    const uint32_t **read_ids, uint32_t *n_blocks, const char **seed_ids);
+
 /* Engine options: "pair_info" (0/1, keep per-pair diagnostics; default 1), "arena_gb" (device
  * memory budget for wave buffers), "max_wave_blocks", "min_wave_blocks", "lanes" (waves in flight,
  * 1..FCX_LANES; with 1 the per-kernel timings of fcx_last_stats are not inflated by overlap),

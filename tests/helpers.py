@@ -19,14 +19,28 @@ class OracleEngine:
     def consensus_blocks(self, blocks, min_cov, min_idt, K=8):
         return [self.oracle.generate_consensus([self.pool[i] for i in b], min_cov, min_idt, K) for b in blocks]
 
+    # raw (pointer / numpy) surface used by the native-parser path of the CLI
+    def upload_pool_raw(self, bases_ptr, offsets):
+        import ctypes as C
+        self.pool = [C.string_at(bases_ptr + int(offsets[i]), int(offsets[i + 1] - offsets[i]))
+                     for i in range(len(offsets) - 1)]
+
+    def consensus_blocks_raw(self, block_off, read_ids, min_cov, min_idt, K=8):
+        import numpy as np
+        blocks = [read_ids[int(block_off[b]):int(block_off[b + 1])].tolist() for b in range(len(block_off) - 1)]
+        cns = self.consensus_blocks(blocks, min_cov, min_idt, K)
+        off = np.zeros(len(cns) + 1, dtype=np.uint64)
+        np.cumsum([len(c) for c in cns], out=off[1:])
+        return np.frombuffer(b"".join(cns), dtype=np.uint8), off
+
 
 def golden_cases():
     return json.load(open(os.path.join(GOLDEN, "manifest.json")))
 
 
-def run_cli(argv, stdin_bytes, engine):
+def run_cli(argv, stdin_bytes, engine, python_parser=False):
     from falcon_b200 import consensus
-    args = consensus.parse_args(["consensus"] + list(argv))
+    args = consensus.parse_args(["consensus"] + list(argv) + (["--python-parser"] if python_parser else []))
     out = io.StringIO()
     consensus.run(args, stdin=io.BytesIO(stdin_bytes), stdout=out, engine=engine)
     return out.getvalue().encode()

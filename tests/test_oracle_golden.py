@@ -17,7 +17,9 @@ def test_cli_with_oracle_matches_reference_golden(name, oracle):
     assert hashlib.md5(stdin).hexdigest() == case["in_md5"]
     want = open(os.path.join(GOLDEN, name + ".out"), "rb").read()
     assert hashlib.md5(want).hexdigest() == case["out_md5"]
-    got = run_cli(case["args"], stdin, OracleEngine(oracle))
+    got = run_cli(case["args"], stdin, OracleEngine(oracle))                       # native parser
+    assert got == want
+    got = run_cli(case["args"], stdin, OracleEngine(oracle), python_parser=True)   # Python restatement
     assert got == want
 
 
@@ -50,3 +52,67 @@ def test_parser_block_rules():
     assert [sid for _, sid in blocks] == ["s1", "y1"]
     assert blocks[0][0] == [b"ACGT", b"ACGT", b"AAAA", b"GG"]
     assert len(blocks[1][0][0]) == 99999 and len(blocks[1][0]) == 2
+
+
+def _python_blocks(txt, min_n_read, min_len_aln, max_n_read, min_cov_aln, max_cov_aln):
+    import io
+    from falcon_b200 import consensus
+    cfg = (4, 8, max_n_read, 0.7, 1000, 50, min_cov_aln, max_cov_aln)
+    return [(sid, seqs) for seqs, sid in consensus.get_seq_data(io.BytesIO(txt), cfg, min_n_read, min_len_aln)]
+
+
+def _native_blocks(txt, min_n_read, min_len_aln, max_n_read, min_cov_aln, max_cov_aln, chunk):
+    import ctypes as C
+    from falcon_b200.binding import StreamParser
+    ps = StreamParser(min_n_read, min_len_aln, max_n_read, min_cov_aln, max_cov_aln)
+    out = []
+    pos = 0
+    while True:
+        piece = txt[pos:pos + chunk]
+        pos += chunk
+        eof = pos >= len(txt)
+        n = ps.feed(piece, eof)
+        while n > 0:
+            ptr, off, boff, rids, ids = ps.take(3, 1 << 20)
+            for b, sid in enumerate(ids):
+                seqs = [C.string_at(ptr + int(off[r]), int(off[r + 1] - off[r])) for r in rids[int(boff[b]):int(boff[b + 1])]]
+                out.append((sid, seqs))
+            n = ps.pending()
+        if eof or ps.stopped:
+            break
+    return out
+
+
+def test_native_parser_matches_python_restatement():
+    """fcx_parser_* vs the Python get_seq_data + get_longest_reads on tricky streams, with the
+    stream cut at arbitrary chunk boundaries."""
+    import random
+    rnd = random.Random(5)
+    def seq(n):
+        return "".join(rnd.choice("ACGT") for _ in range(n))
+    lines = []
+    for b in range(12):
+        n = rnd.randint(0, 9)
+        sid = "seed%d" % b
+        lines.append("%s %s" % (sid, seq(rnd.randint(5, 400))))
+        for r in range(n):
+            rid = rnd.choice(["r%d_%d" % (b, r), "r%d_%d" % (b, max(0, r - 1)), sid])   # duplicates
+            lines.append("%s  \t %s  " % (rid, seq(rnd.randint(1, 500))))
+        if rnd.random() < 0.2:
+            lines.append("garbage with four tokens here")
+        if rnd.random() < 0.2:
+            lines.append("")
+        lines.append(rnd.choice(["+ +", "+ +", "+ +", "* *", "+ x"]))
+    lines.append("big " + "A" * 100007)
+    lines.append("other " + "C" * 100000)
+    lines.append("+ +")
+    lines.append("- -")
+    lines.append("after %s" % seq(50))
+    lines.append("+ +")
+    txt = ("\n".join(lines) + "\n").encode()
+    for params in ((1, 0, 500, 0, 0), (3, 50, 4, 0, 0), (2, 0, 500, 1, 2), (1, 0, 3, 0, 1)):
+        want = _python_blocks(txt, *params)
+        for chunk in (7, 1000, 1 << 20):
+            got = _native_blocks(txt, *params, chunk)
+            assert got == want, (params, chunk)
+    assert len(_python_blocks(txt, 1, 0, 500, 0, 0)) >= 5
