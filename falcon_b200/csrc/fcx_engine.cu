@@ -294,7 +294,7 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
     if (ctx->debug_split_above && nb > ctx->debug_split_above) { L.err = "out of device memory (simulated)"; return 100; }
     std::vector<BlockDesc> hb(nb);
     uint64_t npairs64 = 0, kpos_total = 0, rec_total = 0, cns_total = 0, m_total = 0, tiles = 0;
-    uint32_t max_np = 1;
+    uint32_t max_np = 1; int max_slen = 1, max_rlen = 1;
     for (uint32_t b = 0; b < nb; b++) {
         uint32_t lo = block_off[b0 + b], hi = block_off[b0 + b + 1];
         BlockDesc& d = hb[b];
@@ -313,6 +313,7 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
         d.tile_begin = (uint32_t)tiles; tiles += (uint64_t)((d.slen + 31) / 32) * (d.rb_pad / 32);
         npairs64 += d.n_pairs;
         max_np = std::max(max_np, d.n_pairs);
+        max_slen = std::max(max_slen, d.slen);
     }
     const uint32_t np = (uint32_t)npairs64;
     std::vector<PairDesc> hp(np);
@@ -322,6 +323,7 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
             uint32_t rid = read_ids[lo + 1 + j];
             PairDesc& pd = hp[hb[b].pair_begin + j];
             pd.read_woff = ctx->h_woff[rid]; pd.block = b; pd.rlen = ctx->h_len[rid];
+            max_rlen = std::max(max_rlen, pd.rlen);
         }
     }
     cudaStream_t st = L.stream;
@@ -358,11 +360,15 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
     L.counters[FCX_C_KERNEL_LAUNCHES] += 1;
     // ---- range
     if (np) {
-        const unsigned rgrid = std::min<unsigned>((np + RANGE_WARPS - 1) / RANGE_WARPS, (unsigned)ctx->sm_count * 3u);
+        // histogram bins actually needed by this wave (diagonal range <= read + seed length)
+        const int bins = std::min(RANGE_BINS, (max_rlen + max_slen) / BIN_SIZE + 8);
+        const size_t rsmem = (size_t)RANGE_WARPS * bins * sizeof(int);
+        const unsigned per_sm = (unsigned)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / std::max<size_t>(rsmem, 1)));
+        const unsigned rgrid = std::min<unsigned>((np + RANGE_WARPS - 1) / RANGE_WARPS, (unsigned)ctx->sm_count * per_sm);
         CKR(L.d_rlist.reserve((size_t)rgrid * RANGE_WARPS * RANGE_LIST_CAP * sizeof(int2)));
-        k_range<<<rgrid, RANGE_WARPS * 32, RANGE_WARPS * RANGE_BINS * sizeof(int), st>>>(
+        k_range<<<rgrid, RANGE_WARPS * 32, rsmem, st>>>(
             L.d_blocks.as<BlockDesc>(), L.d_pairs.as<PairDesc>(), np, pool, L.d_ktab.as<uint32_t>(),
-            L.d_kpos.as<uint32_t>(), L.d_rlist.as<int2>(), L.d_ranges.as<PairRange>());
+            L.d_kpos.as<uint32_t>(), L.d_rlist.as<int2>(), bins, L.d_ranges.as<PairRange>());
         CKL(cudaGetLastError());
         L.counters[FCX_C_KERNEL_LAUNCHES] += 1;
         CKL(cudaMemcpyAsync(L.h_ranges.p, L.d_ranges.p, (size_t)np * sizeof(PairRange), cudaMemcpyDeviceToHost, st));
@@ -380,7 +386,7 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
             // Only accepted pairs are traced back, and acceptance needs D / A < max_diff with
             // A = (q_e + t_e + D) / 2 <= (q + t + D) / 2, i.e. D < max_diff (q + t) / (2 - max_diff):
             // steps beyond that bound need no trace record.
-            const double mdiff = 1.0 - min_idt;
+            const double mdiff = std::max(0.0, 1.0 - min_idt);
             uint64_t md = max_d_of(ql, tl);
             if (mdiff < 1.999) md = std::min<uint64_t>(md, (uint64_t)(mdiff * (ql + tl) / (2.0 - mdiff)) + 2);
             ha[p].trace_cap = (uint32_t)(md + 1); ha[p].pad_ = 0;
@@ -550,7 +556,7 @@ extern "C" int fcx_consensus_blocks(fcx_ctx* ctx, uint32_t n_blocks, const uint3
         while (e < n_blocks) {
             uint32_t lo = block_off[e], hi = block_off[e + 1];
             int slen = ctx->h_len[read_ids[lo]];
-            const double mdiff = 1.0 - min_idt;
+            const double mdiff = std::max(0.0, 1.0 - min_idt);
             const double capfrac = std::min(0.3, mdiff < 1.999 ? mdiff / (2.0 - mdiff) : 0.3);
             double bb = (double)KTAB * 4 + (double)slen * (4 + 8 * 12 + 2 * 5) + 4.0 * slen * (((hi - lo - 1) + 31) & ~31u);
             for (uint32_t i = lo + 1; i < hi; i++) {

@@ -318,11 +318,11 @@ constexpr int RANGE_LIST_CAP = 16384;
 __global__ void __launch_bounds__(RANGE_WARPS * 32)
 k_range(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs, uint32_t n_pairs,
         const uint32_t* __restrict__ pool, const uint32_t* __restrict__ ktab,
-        const uint32_t* __restrict__ kpos_arena, int2* __restrict__ list_scratch,
+        const uint32_t* __restrict__ kpos_arena, int2* __restrict__ list_scratch, int bins,
         PairRange* __restrict__ out) {
     extern __shared__ int s_hist_all[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    int* hist = s_hist_all + wib * RANGE_BINS;
+    int* hist = s_hist_all + wib * bins;      // bins >= (max read len + max seed len) / 48 + 2 for this wave
     const uint32_t gw = blockIdx.x * RANGE_WARPS + wib, nw = gridDim.x * RANGE_WARPS;
     int2* list = list_scratch + (size_t)gw * RANGE_LIST_CAP;
     const unsigned lt = lanemask_lt();
@@ -728,16 +728,26 @@ __global__ void k_traceback(const BlockDesc* __restrict__ blocks, const PairDesc
     // (1) backwards: bit d of path = step d came from k+1 (a target-only column)
     int k = a.k_end;
     uint32_t acc = 0;
-    for (int d = D; d >= 1; d--) {
+    // the record addresses do not depend on the path (only the bit inside does), so the headers
+    // are fetched four steps ahead to overlap the DRAM latency of this pointer chase
+    auto step_back = [&](const int d, const uint2 hd) {
         const uint32_t* rec = trace + (size_t)d * TRACE_REC_WORDS;
-        const uint2 hd = __ldg(reinterpret_cast<const uint2*>(rec));       // {min_k, first ballot word}
         const int idx = (k - (int)hd.x) >> 1;
         const uint32_t w = idx < 32 ? hd.y : __ldg(rec + 1 + (idx >> 5));
         const uint32_t up = (w >> (idx & 31)) & 1u;
         acc |= up << (d & 31);
         if ((d & 31) == 0 || d == 1) { path[d >> 5] = acc; acc = 0; }
         k += up ? 1 : -1;
+    };
+    int d = D;
+    for (; d >= 4; d -= 4) {
+        const uint2 h0 = __ldg(reinterpret_cast<const uint2*>(trace + (size_t)d * TRACE_REC_WORDS));
+        const uint2 h1 = __ldg(reinterpret_cast<const uint2*>(trace + (size_t)(d - 1) * TRACE_REC_WORDS));
+        const uint2 h2 = __ldg(reinterpret_cast<const uint2*>(trace + (size_t)(d - 2) * TRACE_REC_WORDS));
+        const uint2 h3 = __ldg(reinterpret_cast<const uint2*>(trace + (size_t)(d - 3) * TRACE_REC_WORDS));
+        step_back(d, h0); step_back(d - 1, h1); step_back(d - 2, h2); step_back(d - 3, h3);
     }
+    for (; d >= 1; d--) step_back(d, __ldg(reinterpret_cast<const uint2*>(trace + (size_t)d * TRACE_REC_WORDS)));
     // (2) forwards.  ent[] was pre-filled with ENT_PLAIN (= a match column without insertions), so
     // only the other columns are written: target-only columns and columns followed by query-only
     // columns.  xam[] (query index at the column, used by the rare generic consensus path to fetch
