@@ -92,7 +92,6 @@ def get_seq_data(stream, config, min_n_read, min_len_aln) -> Iterator[Tuple[List
 def get_alignment(seq1: bytes, seq0: bytes, edge_tolerance=1000):
     """K-mer range of seq1 on seq0 for the --trim path -- consensus.py:48-99."""
     from . import binding
-    import ctypes as C
     kup = binding.kup()
     lk_ptr = kup.allocate_kmer_lookup(1 << (K * 2))
     sa_ptr = kup.allocate_seq(len(seq0))

@@ -307,7 +307,6 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
         d.rec_cap = (uint32_t)std::max<int64_t>(64, (int64_t)d.slen * 8 + 64);
         d.rec_off = rec_total; rec_total += d.rec_cap;
         d.cns_off = cns_total; cns_total += (uint64_t)d.slen * 2 + 8;
-        d.cov_off = 0;
         d.rb_pad = (d.n_pairs + 31u) & ~31u;
         d.m_off = m_total; m_total += (uint64_t)d.rb_pad * (uint64_t)std::max(d.slen, 1);
         d.tile_begin = (uint32_t)tiles; tiles += (uint64_t)((d.slen + 31) / 32) * (d.rb_pad / 32);

@@ -25,7 +25,6 @@ constexpr int BIN_SIZE = 48;            // K * INDEL_ALLOWENCE_0 (falcon.c:602-6
 constexpr int COUNT_TH = 5;             // falcon.c:604
 constexpr int BAND_TOL = 150;           // INDEL_ALLOWENCE_2 (falcon.c:624)
 constexpr int TRACE_REC_WORDS = 8;      // one 32-byte sector per d step: [min_k, w0..w4, pad, pad]
-constexpr int MAX_BAND_WORDS = 5;       // band <= 151 cells -> 5 ballot words
 constexpr unsigned FULL = 0xffffffffu;
 
 struct BlockDesc {
@@ -33,7 +32,6 @@ struct BlockDesc {
     uint64_t kpos_off;    // offset (entries) into the kpos arena
     uint64_t rec_off;     // offset (records) into the consensus record arena
     uint64_t cns_off;     // offset (bytes) into the consensus output arena
-    uint64_t cov_off;     // offset (entries) into the coverage arena
     uint32_t pair_begin;  // first pair of this block (wave-local pair index)
     uint32_t n_pairs;     // n_seq - 1
     int32_t  slen;        // seed length

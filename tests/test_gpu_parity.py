@@ -255,3 +255,30 @@ def test_wave_split_on_out_of_memory(oracle):
     b = e.consensus_blocks(blocks, 4, 0.70)
     assert a == b and e.stats()["waves"] >= 5
     assert len(e.pair_info()) == S.n_pairs
+
+
+def test_unaligned_and_rejected_pairs(engine, oracle):
+    """Pairs that pass the k-mer filter but (a) blow the DP band (a 200-base insertion) or (b) align
+    with identity below min_idt (their DP runs past the trace bound kept for acceptable pairs)
+    must be reported exactly like the reference and must not disturb the block's consensus."""
+    rng = np.random.default_rng(29)
+    g = synth.random_codes(7000, rng)
+    seed = synth.codes_to_bytes(g)
+    good = [synth.codes_to_bytes(synth.add_errors(g, rng)) for _ in range(8)]
+    band = synth.codes_to_bytes(np.concatenate([g[:3500], synth.random_codes(200, rng), g[3500:]]))
+    noisy = [synth.codes_to_bytes(synth.add_errors(g, rng, 0.20, 0.12, 0.06)) for _ in range(4)]
+    seqs = [seed, seed] + good[:4] + [band] + noisy + good[4:]
+    saw_unaligned = saw_rejected = False
+    for min_idt in (0.70, 0.80, 0.55):
+        engine.upload_pool(seqs)
+        got = engine.consensus_blocks([list(range(len(seqs)))], 3, min_idt)[0]
+        info = engine.pair_info()
+        want, oinfo = oracle.generate_consensus(seqs, 3, min_idt, want_info=True)
+        for j, (g_, o_) in enumerate(zip(info, oinfo[1:])):
+            assert (g_.passed_filter, g_.aligned, g_.accepted) == (o_.passed_filter, o_.aligned, o_.accepted), j
+            if o_.aligned:
+                assert (g_.dist, g_.aln_size, g_.q_e, g_.t_e, g_.trace_cells) == (o_.dist, o_.aln_size, o_.q_e, o_.t_e, o_.trace_cells), j
+        assert got == want
+        saw_unaligned |= any(o.passed_filter and not o.aligned for o in oinfo[1:])
+        saw_rejected |= any(o.aligned and not o.accepted for o in oinfo[1:])
+    assert saw_unaligned and saw_rejected
