@@ -544,8 +544,12 @@ extern "C" int fcx_consensus_blocks(fcx_ctx* ctx, uint32_t n_blocks, const uint3
     // Aim for >= 2 waves per lane so that stages of different waves overlap, but keep waves large
     // enough (min_wave_blocks) for the one-warp-per-block consensus kernel to fill the GPU.
     const int nl = ctx->active_lanes > 0 ? ctx->active_lanes : (int)ctx->lanes.size();
+    // equal-sized waves: at least one per lane, none larger than max_wave_blocks (a short last wave
+    // would still pay the full, latency-bound consensus kernel)
     const int wpl = getenv("FCX_WAVES_PER_LANE") ? std::max(1, atoi(getenv("FCX_WAVES_PER_LANE"))) : 1;
-    uint32_t target = (n_blocks + wpl * nl - 1) / (wpl * nl);
+    uint32_t n_waves = std::max<uint32_t>((uint32_t)(wpl * nl), (n_blocks + ctx->max_wave_blocks - 1) / ctx->max_wave_blocks);
+    n_waves = ((n_waves + nl - 1) / nl) * nl;                       // a multiple of the lane count
+    uint32_t target = (n_blocks + n_waves - 1) / std::max(1u, n_waves);
     target = std::max(target, ctx->min_wave_blocks);
     target = std::min(target, ctx->max_wave_blocks);
     const double budget = (double)ctx->arena_budget / nl;
