@@ -755,6 +755,19 @@ __global__ void k_traceback(const BlockDesc* __restrict__ blocks, const PairDesc
     uint32_t pend = 0; int pend_y = -1, pend_x = 0;   // entry of the last target column, still open
     uint32_t pw = 0;
     xam[0] = 1u;                                      // column 0 is always a match at x = 0
+    // x and y creep forward a few bases per step: keep the current two packed words of each
+    // sequence in registers and reload only when the position crosses a word boundary
+    int wq_i = -2, wt_i = -2; uint32_t wq_lo = 0, wq_hi = 0, wt_lo = 0, wt_hi = 0;
+    auto win_q = [&](const int pos) -> uint32_t {
+        const int wi = pos >> 4;
+        if (wi != wq_i) { wq_i = wi; wq_lo = __ldg(q + wi); wq_hi = __ldg(q + wi + 1); }
+        return __funnelshift_r(wq_lo, wq_hi, (pos & 15) << 1);
+    };
+    auto win_t = [&](const int pos) -> uint32_t {
+        const int wi = pos >> 4;
+        if (wi != wt_i) { wt_i = wi; wt_lo = __ldg(t + wi); wt_hi = __ldg(t + wi + 1); }
+        return __funnelshift_r(wt_lo, wt_hi, (pos & 15) << 1);
+    };
     for (int d = 0; d <= D; d++) {
         if (d > 0) {
             if ((d & 31) == 0 || d == 1) pw = path[d >> 5];
@@ -765,7 +778,7 @@ __global__ void k_traceback(const BlockDesc* __restrict__ blocks, const PairDesc
                 }
                 pend = ENT_VALID; pend_y = y; pend_x = x; y++; run = 0;
             } else {                                  // query-only column
-                if (run < ENT_INS_INLINE) pend |= (uint32_t)base_at(q, qs + x) << (2 * run);
+                if (run < ENT_INS_INLINE) pend |= (win_q(qs + x) & 3u) << (2 * run);
                 x++; run++;
                 if (run == 255) {            // the 255th consecutive query-only column: tags stop before it
                     t_cnt = y;               // target positions 0..y-1 carry tags
@@ -779,7 +792,7 @@ __global__ void k_traceback(const BlockDesc* __restrict__ blocks, const PairDesc
         for (;;) {
             int rem = min(q_len - x - adv, t_len - y - adv);
             if (rem <= 0) break;
-            uint32_t diff = fetch16(q, qs + x + adv) ^ fetch16(t, ts + y + adv);
+            uint32_t diff = win_q(qs + x + adv) ^ win_t(ts + y + adv);
             int n = diff ? (__ffs(diff) - 1) >> 1 : 16;
             n = min(n, rem);
             adv += n;
