@@ -185,8 +185,8 @@ constexpr int RANGE_BINS = 4224;   // >= (99999 + 99999) / 48 + 1
 // Slow path (match list does not fit the per-warp scratch): every pass re-walks the buckets.
 __device__ void range_pair_slow(const uint32_t* __restrict__ read, const uint32_t* __restrict__ tab,
                                 const uint32_t* __restrict__ kpos, const int nq, int* hist, const int lane,
-                                PairRange* __restrict__ outp) {
-    PairRange* out = outp; const int p = 0;
+                                PairRange* __restrict__ out) {
+    const int p = 0;               // `out` already points at this pair's slot
     PairRange r; r.s1 = r.e1 = r.s2 = r.e2 = 0; r.n_match = 0; r.pass = 0;
 
     // ---- pass A
