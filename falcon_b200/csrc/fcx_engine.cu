@@ -57,7 +57,7 @@ struct Lane {                 // one in-flight wave: stream, events, buffers, st
     cudaStream_t stream_hi = nullptr;   // high priority: the latency-bound consensus kernel
     cudaEvent_t ev[8] = {nullptr};
     DevBuf d_blocks, d_pairs, d_ranges, d_allocs, d_aln, d_ktab, d_kpos, d_trace, d_path, d_xam, d_ent, d_M,
-           d_rlist, d_recs, d_lvl, d_meta, d_cns, d_eqv, d_cnsout;
+           d_rlist, d_recs, d_lvl, d_meta, d_cns, d_eqv, d_cnsout, d_order;
     HostBuf h_ranges, h_aln, h_cns, h_cnsout, h_eqv;
     std::string err;
     double times[FCX_T_COUNT] = {0};
@@ -65,7 +65,7 @@ struct Lane {                 // one in-flight wave: stream, events, buffers, st
     double prof[8] = {0};
     void release() {
         DevBuf* bufs[] = {&d_blocks, &d_pairs, &d_ranges, &d_allocs, &d_aln, &d_ktab, &d_kpos, &d_trace, &d_path,
-                          &d_xam, &d_ent, &d_M, &d_rlist, &d_recs, &d_lvl, &d_meta, &d_cns, &d_eqv, &d_cnsout};
+                          &d_xam, &d_ent, &d_M, &d_rlist, &d_recs, &d_lvl, &d_meta, &d_cns, &d_eqv, &d_cnsout, &d_order};
         for (auto* b : bufs) b->release();
         HostBuf* hb[] = {&h_ranges, &h_aln, &h_cns, &h_cnsout, &h_eqv};
         for (auto* b : hb) b->release();
@@ -115,6 +115,7 @@ struct fcx_ctx {
     uint32_t min_wave_blocks = 384;
     int n_lanes = 2;
     int active_lanes = 0;              // 0 = all
+    bool dp_half = true;               // k_dp2: two pairs per warp (default); false = one warp per pair (k_dp)
     bool dp_staged = false;            // TMA-staged k_dp variant (FCX_DP_STAGED=1 / option "dp_staged")
     uint32_t debug_split_above = 0;    // test hook: pretend waves with more blocks than this do not fit
 };
@@ -178,6 +179,7 @@ extern "C" int fcx_create(int device, fcx_ctx** out) {
     if (const char* s = getenv("FCX_LANES")) ctx->n_lanes = std::max(1, atoi(s));
     if (const char* s = getenv("FCX_PROFILE")) ctx->profile = atoi(s) != 0;
     if (const char* s = getenv("FCX_DP_STAGED")) ctx->dp_staged = atoi(s) != 0;
+    if (const char* s = getenv("FCX_DP_HALF")) ctx->dp_half = atoi(s) != 0;
     cudaFuncSetAttribute(k_dp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (!getenv("FCX_WAVE_BLOCKS")) ctx->max_wave_blocks = (uint32_t)(ctx->sm_count * CNS_CTAS_PER_SM * CNS_WARPS);
@@ -231,6 +233,7 @@ extern "C" int fcx_set_option(fcx_ctx* ctx, const char* name, double value) {
     else if (n == "max_wave_blocks") ctx->max_wave_blocks = (uint32_t)value;
     else if (n == "min_wave_blocks") ctx->min_wave_blocks = (uint32_t)value;
     else if (n == "dp_staged") ctx->dp_staged = value != 0;
+    else if (n == "dp_half") ctx->dp_half = value != 0;
     else if (n == "debug_split_above") ctx->debug_split_above = (uint32_t)value;
     else if (n == "lanes") ctx->active_lanes = value <= 0 ? 0 : std::min((int)value, (int)ctx->lanes.size());
     else { ctx->err = "unknown option: " + n; return 1; }
@@ -403,6 +406,32 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
     // ---- DP
     CKL(cudaEventRecord(L.ev[3], st));
     if (np) {
+        if (ctx->dp_half && !ctx->dp_staged) {
+            // two pairs per warp, pairs ordered by span (counting sort, 64-base buckets) so that the
+            // halves of a warp and the warps of a CTA carry similar work
+            std::vector<uint32_t> ord; ord.reserve(dp_pairs);
+            {
+                const uint32_t NB = 200000 / 64 + 2;
+                std::vector<uint32_t> cnt(NB + 1, 0);
+                for (uint32_t pp = 0; pp < np; pp++) if (hr[pp].pass) cnt[NB - 1 - (uint32_t)((hr[pp].e1 - hr[pp].s1 + hr[pp].e2 - hr[pp].s2) / 64)]++;
+                uint32_t run = 0;
+                for (uint32_t b = 0; b <= NB; b++) { uint32_t c = cnt[b]; cnt[b] = run; run += c; }
+                ord.resize(dp_pairs);
+                for (uint32_t pp = 0; pp < np; pp++) if (hr[pp].pass) ord[cnt[NB - 1 - (uint32_t)((hr[pp].e1 - hr[pp].s1 + hr[pp].e2 - hr[pp].s2) / 64)]++] = pp;
+            }
+            CKR(L.d_order.reserve(std::max<size_t>(1, ord.size()) * 4));
+            CKL(cudaMemcpyAsync(L.d_order.p, ord.data(), ord.size() * 4, cudaMemcpyHostToDevice, st));
+            CKL(cudaMemsetAsync(L.d_aln.p, 0, (size_t)np * sizeof(PairAln), st));     // pairs that failed the filters
+            const uint32_t n_dp = (uint32_t)ord.size();
+            if (n_dp) {
+                const uint32_t per_cta = DP2_WARPS * 2;
+                k_dp2<<<(n_dp + per_cta - 1) / per_cta, DP2_WARPS * 32, 0, st>>>(
+                    L.d_blocks.as<BlockDesc>(), L.d_pairs.as<PairDesc>(), L.d_ranges.as<PairRange>(),
+                    L.d_allocs.as<PairAlloc>(), L.d_order.as<uint32_t>(), n_dp, pool, L.d_trace.as<uint32_t>(),
+                    1.0 - min_idt, L.d_aln.as<PairAln>());
+            }
+            // (the pageable-source cudaMemcpyAsync above has staged `ord` before returning)
+        } else {
         // staged variant: spans copied to shared memory by TMA when they fit the per-CTA budget
         const int stage_words = (int)(((max_span + 15) / 16 + 1 + 8 + 3) & ~3u);
         const size_t smem_staged = (size_t)DP_WARPS * ((size_t)VRING * 4 + (size_t)stage_words * 8 + 16);
@@ -417,6 +446,7 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
                 L.d_blocks.as<BlockDesc>(), L.d_pairs.as<PairDesc>(), L.d_ranges.as<PairRange>(),
                 L.d_allocs.as<PairAlloc>(), np, pool, L.d_trace.as<uint32_t>(), 1.0 - min_idt, 0,
                 L.d_aln.as<PairAln>());
+        }
         }
         CKL(cudaGetLastError());
         L.counters[FCX_C_KERNEL_LAUNCHES] += 1;
