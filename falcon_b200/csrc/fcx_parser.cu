@@ -20,9 +20,13 @@
 
 namespace {
 
+struct Rd { uint64_t off; uint32_t len; };
+
 struct Block {
     std::string seed_id;
-    std::vector<std::string> seqs;     // [0] = seed, after get_longest_reads
+    std::vector<char> data;            // read bytes in arrival order, back to back (the seed once)
+    std::vector<Rd> reads;             // distinct reads in arrival order; reads[0] is the seed
+    std::vector<uint32_t> order;       // the block as generate_consensus sees it: indices into reads
 };
 
 inline bool is_space(unsigned char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\v' || c == '\f'; }
@@ -33,9 +37,10 @@ struct fcx_parser {
     unsigned min_n_read, min_len_aln, max_n_read, min_cov_aln, max_cov_aln;
     std::string carry;                 // partial last line of the previous chunk
     bool stopped = false;
-    // block under construction
-    std::vector<std::string> seqs;
-    std::string seed_id;
+    // block under construction.  seqs = [seed, seed, r1, r2, ...] in the reference; here the seed
+    // is stored once and referenced twice.
+    Block cur;
+    size_t n_seqs = 0;                 // len(seqs) of the reference (seed counted twice)
     size_t seed_len = 0;
     unsigned long long read_cov = 0;
     std::unordered_set<std::string> ids;
@@ -45,34 +50,44 @@ struct fcx_parser {
     std::vector<uint64_t> o_off;
     std::vector<uint32_t> o_boff, o_rids;
 
-    void reset_block() { seqs.clear(); ids.clear(); seed_id.clear(); read_cov = 0; }
+    void reset_block() {
+        cur.seed_id.clear(); cur.data.clear(); cur.reads.clear(); cur.order.clear();
+        ids.clear(); n_seqs = 0; read_cov = 0;
+    }
 
     void emit_block() {
-        if (seqs.empty()) return;      // reference: ZeroDivisionError territory (read_cov // 0); skipped here
-        if (!(seqs.size() >= min_n_read && read_cov / seed_len >= min_cov_aln)) return;
-        // get_longest_reads(sort=True)
-        std::stable_sort(seqs.begin() + 1, seqs.end(),
-                         [](const std::string& a, const std::string& b) { return a.size() > b.size(); });
+        if (n_seqs == 0) return;       // reference: ZeroDivisionError territory (read_cov // 0); skipped here
+        if (!(n_seqs >= min_n_read && read_cov / seed_len >= min_cov_aln)) return;
+        // seqs[1:] in arrival order: the seed copy is present iff the seed's id was not a duplicate,
+        // which it never is (it is the first id of the block); then the other distinct reads
+        std::vector<uint32_t> rest;
+        rest.reserve(cur.reads.size());
+        for (uint32_t i = 0; i < cur.reads.size(); i++) rest.push_back(i);      // [seed copy, r1, r2, ...]
+        // get_longest_reads(sort=True): stable sort of seqs[1:] by -len
+        std::stable_sort(rest.begin(), rest.end(),
+                         [&](uint32_t a, uint32_t b) { return cur.reads[a].len > cur.reads[b].len; });
         size_t keep = max_n_read;
         if (max_cov_aln > 0) {
             keep = 1; unsigned long long cov = 0;
-            for (size_t i = 1; i < seqs.size(); i++) {
+            for (size_t i = 0; i < rest.size(); i++) {
                 if (cov / seed_len > max_cov_aln) break;
-                keep++; cov += seqs[i].size();
+                keep++; cov += cur.reads[rest[i]].len;
             }
             keep = std::min<size_t>(keep, max_n_read);
         }
-        if (seqs.size() > keep) seqs.resize(keep);
-        Block b; b.seed_id = seed_id; b.seqs = std::move(seqs);
-        ready.push_back(std::move(b));
-        seqs.clear();
+        cur.order.clear();
+        cur.order.push_back(0);                                                  // seqs[0] = seed
+        for (size_t i = 0; i < rest.size() && cur.order.size() < keep; i++) cur.order.push_back(rest[i]);
+        if (keep == 0) cur.order.clear();                                       // seqs[:0]
+        ready.push_back(std::move(cur));
+        cur = Block();
     }
 
     void line(const char* p, size_t n) {
         if (stopped) return;
         // l.strip().split(): tokens separated by ASCII whitespace; exactly two are required
         size_t i = 0;
-        const char* tok[2]; size_t len[2]; int nt = 0;
+        const char* tok[2] = {nullptr, nullptr}; size_t len[2] = {0, 0}; int nt = 0;
         while (i < n) {
             while (i < n && is_space((unsigned char)p[i])) i++;
             if (i >= n) break;
@@ -89,8 +104,14 @@ struct fcx_parser {
         if (!ctrl) {
             if (slen >= min_len_aln) {
                 std::string id(tok[0], len[0]);
-                if (seqs.empty()) { seqs.emplace_back(tok[1], slen); seed_len = slen; seed_id = id; }   // the seed
-                if (ids.insert(id).second) { seqs.emplace_back(tok[1], slen); read_cov += slen; }       // seed again, by design
+                const bool first = n_seqs == 0;
+                if (first) { seed_len = slen; cur.seed_id = id; n_seqs = 1; }                 // the seed
+                if (ids.insert(id).second) {                                                   // seed again, by design
+                    Rd r; r.off = cur.data.size(); r.len = (uint32_t)slen;
+                    cur.data.insert(cur.data.end(), tok[1], tok[1] + slen);
+                    cur.reads.push_back(r);
+                    n_seqs++; read_cov += slen;
+                }
             }
         } else if (tok[0][0] == '+') { emit_block(); reset_block(); }
         else if (tok[0][0] == '*') { reset_block(); }
@@ -139,14 +160,13 @@ extern "C" int fcx_parser_take(fcx_parser* ps, uint32_t max_blocks, uint64_t max
     uint32_t nb = 0; uint64_t total = 0;
     while (!ps->ready.empty() && nb < max_blocks) {
         Block& b = ps->ready.front();
-        uint64_t sz = 0;
-        for (auto& s : b.seqs) sz += s.size();
+        const uint64_t sz = b.data.size();
         if (nb > 0 && total + sz > max_bases) break;
-        for (auto& s : b.seqs) {
-            ps->o_rids.push_back((uint32_t)(ps->o_off.size() - 1));
-            ps->o_bases.insert(ps->o_bases.end(), s.begin(), s.end());
-            ps->o_off.push_back(ps->o_bases.size());
-        }
+        const uint32_t base_id = (uint32_t)(ps->o_off.size() - 1);
+        const uint64_t base_off = ps->o_bases.size();
+        ps->o_bases.insert(ps->o_bases.end(), b.data.begin(), b.data.end());      // one copy per block
+        for (auto& r : b.reads) ps->o_off.push_back(base_off + r.off + r.len);
+        for (uint32_t k : b.order) ps->o_rids.push_back(base_id + k);
         ps->o_boff.push_back((uint32_t)ps->o_rids.size());
         ps->o_ids.insert(ps->o_ids.end(), b.seed_id.begin(), b.seed_id.end());
         ps->o_ids.push_back('\0');

@@ -1,0 +1,36 @@
+"""CPU: the bench.py contract that does not need a GPU -- the reference arm prints one JSON line
+with the agreed keys on a tiny workload, and our arm refuses to run without a CUDA device."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SMALL = ["--genome", "40000", "--read-len", "3000", "--cov", "15", "--blocks", "4", "--cpu-sample-blocks", "3"]
+
+
+def test_reference_arm_json_line():
+    env = dict(os.environ)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "1"] + SMALL, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr.decode()[-500:]
+    line = json.loads(r.stdout.decode().strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "pairs/s" and line["higher_is_better"] is True
+    assert line["metric"].startswith("aligned read-pairs/sec")
+    assert line["value"] > 0 and line["steps"] == 1 and line["warmup"] == 1
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in line["config"]
+
+
+def test_our_arm_needs_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"] + SMALL,
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
+    assert r.returncode != 0
+    assert b"no CUDA device" in r.stderr or b"no CPU path" in r.stderr
