@@ -322,7 +322,8 @@ def main():
                        "bytes_per_pair": k["dram_bytes"] / max(1, k.get("pairs", 1)), "source": "profiles/ncu_summary.json"}
     except Exception:
         pass
-    roofline = {"kernel": "k_" + dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+    kname = {"dp": "k_dp2"}.get(dom, "k_" + dom)      # the default DP kernel is the two-pairs-per-warp k_dp2
+    roofline = {"kernel": kname, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
                 "frac": ach / peak, "traffic": traffic,
                 "kernel_timing": "CUDA events on the launching stream, one step with a single wave in flight",
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
