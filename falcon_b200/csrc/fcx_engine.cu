@@ -307,7 +307,10 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
         d.pair_begin = (uint32_t)npairs64;
         d.n_pairs = hi - lo - 1;
         d.kpos_off = kpos_total; kpos_total += (uint64_t)std::max(d.slen, 1);
-        d.rec_cap = (uint32_t)std::max<int64_t>(64, (int64_t)d.slen * 8 + 64);
+        // consensus column records: live (position, delta, base) columns.  Measured ~4 per position
+        // at 50x; the number grows with coverage (every column needs a vote), hence the n_pairs term.
+        // k_consensus reports an overflow as an error, it never drops a column.
+        d.rec_cap = (uint32_t)std::max<int64_t>(64, (int64_t)d.slen * (8 + (int64_t)d.n_pairs / 16) + 64);
         d.rec_off = rec_total; rec_total += d.rec_cap;
         d.cns_off = cns_total; cns_total += (uint64_t)d.slen * 2 + 8;
         d.rb_pad = (d.n_pairs + 31u) & ~31u;
@@ -591,7 +594,7 @@ extern "C" int fcx_consensus_blocks(fcx_ctx* ctx, uint32_t n_blocks, const uint3
             int slen = ctx->h_len[read_ids[lo]];
             const double mdiff = std::max(0.0, 1.0 - min_idt);
             const double capfrac = std::min(0.3, mdiff < 1.999 ? mdiff / (2.0 - mdiff) : 0.3);
-            double bb = (double)KTAB * 4 + (double)slen * (4 + 8 * 12 + 2 * 5) + 4.0 * slen * (((hi - lo - 1) + 31) & ~31u);
+            double bb = (double)KTAB * 4 + (double)slen * (4 + (8 + (hi - lo - 1) / 16) * 12 + 2 * 5) + 4.0 * slen * (((hi - lo - 1) + 31) & ~31u);
             for (uint32_t i = lo + 1; i < hi; i++) {
                 // typical aligned span ~ 0.65 x the shorter sequence (exact sizes follow k_range;
                 // an under-estimate is caught by the out-of-memory split below)

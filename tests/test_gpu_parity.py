@@ -282,3 +282,14 @@ def test_unaligned_and_rejected_pairs(engine, oracle):
         saw_unaligned |= any(o.passed_filter and not o.aligned for o in oinfo[1:])
         saw_rejected |= any(o.aligned and not o.accepted for o in oinfo[1:])
     assert saw_unaligned and saw_rejected
+
+
+def test_deep_coverage_default_error_model(engine, oracle):
+    """~500 reads over a 3 kb seed at 15 % error: many live insertion columns per position (the
+    consensus record store scales with coverage); must stay exact."""
+    S = synth.make_set(30000, 3000, 480, seed=43, n_blocks=2, block_stride=900, max_n_read=500, min_ovl=500)
+    assert max(len(b) for b in S.blocks) > 400
+    engine.upload_pool(S.pool)
+    got = engine.consensus_blocks([b.tolist() for b in S.blocks], 6, 0.70)
+    for bi in range(len(S.blocks)):
+        assert got[bi] == oracle.generate_consensus(S.block_seqs(bi), 6, 0.70)
