@@ -86,3 +86,24 @@ def test_long_insertion_delta_wrap(oracle, ref):
     reads.append(synth.codes_to_bytes(synth.add_errors(g, rng, 0.02, 0.01, 0.005)))
     seqs = [seed] + reads
     assert oracle.generate_consensus(seqs, 2, 0.70) == ref.generate_consensus(seqs, 2, 0.70)
+
+
+def test_randomised_blocks_match_reference(oracle, ref):
+    """A sweep over error mixes, read-length spreads, coverages and min_cov/min_idt settings: the
+    restatement must track the compiled reference on every block (consensus + eqv)."""
+    rng = np.random.default_rng(77)
+    n = 0
+    for trial in range(10):
+        p_ins, p_del, p_sub = (float(x) for x in rng.uniform([0.02, 0.01, 0.0], [0.12, 0.08, 0.05]))
+        S = synth.make_set(int(rng.integers(20000, 50000)), int(rng.integers(1500, 5000)), float(rng.uniform(8, 35)),
+                           seed=int(rng.integers(1, 10**6)), n_blocks=3, len_sigma=float(rng.choice([0.0, 0.3, 0.6])),
+                           p_ins=p_ins, p_del=p_del, p_sub=p_sub, block_stride=int(rng.integers(1, 6)),
+                           max_n_read=int(rng.choice([8, 40, 200])))
+        min_cov = int(rng.integers(0, 7)); min_idt = float(rng.choice([0.6, 0.7, 0.8, 0.9]))
+        for bi in range(len(S.blocks)):
+            seqs = S.block_seqs(bi)
+            want = ref.generate_consensus(seqs, min_cov, min_idt, want_eqv=True)
+            got = oracle.generate_consensus(seqs, min_cov, min_idt, want_eqv=True)
+            assert got[0] == want[0] and got[1] == want[1], (trial, bi)
+            n += 1
+    assert n == 30
