@@ -57,7 +57,7 @@ struct Lane {                 // one in-flight wave: stream, events, buffers, st
     cudaStream_t stream_hi = nullptr;   // high priority: the latency-bound consensus kernel
     cudaEvent_t ev[8] = {nullptr};
     DevBuf d_blocks, d_pairs, d_ranges, d_allocs, d_aln, d_ktab, d_kpos, d_trace, d_path, d_xam, d_ent, d_M,
-           d_rlist, d_recs, d_lvl, d_meta, d_cns, d_eqv, d_cnsout, d_order;
+           d_rlist, d_recs, d_lvl, d_meta, d_cns, d_eqv, d_cnsout;
     HostBuf h_ranges, h_aln, h_cns, h_cnsout, h_eqv;
     std::string err;
     double times[FCX_T_COUNT] = {0};
@@ -65,7 +65,7 @@ struct Lane {                 // one in-flight wave: stream, events, buffers, st
     double prof[8] = {0};
     void release() {
         DevBuf* bufs[] = {&d_blocks, &d_pairs, &d_ranges, &d_allocs, &d_aln, &d_ktab, &d_kpos, &d_trace, &d_path,
-                          &d_xam, &d_ent, &d_M, &d_rlist, &d_recs, &d_lvl, &d_meta, &d_cns, &d_eqv, &d_cnsout, &d_order};
+                          &d_xam, &d_ent, &d_M, &d_rlist, &d_recs, &d_lvl, &d_meta, &d_cns, &d_eqv, &d_cnsout};
         for (auto* b : bufs) b->release();
         HostBuf* hb[] = {&h_ranges, &h_aln, &h_cns, &h_cnsout, &h_eqv};
         for (auto* b : hb) b->release();
@@ -115,8 +115,7 @@ struct fcx_ctx {
     uint32_t min_wave_blocks = 384;
     int n_lanes = 2;
     int active_lanes = 0;              // 0 = all
-    bool dp_half = true;               // k_dp2: two pairs per warp (default); false = one warp per pair (k_dp)
-    bool dp_staged = false;            // TMA-staged k_dp variant (FCX_DP_STAGED=1 / option "dp_staged")
+    int dp_variant = 3;                // 3: k_dp3 (default); 1: k_dp (round-1 kernel); 2: k_dp with TMA-staged spans
     uint32_t debug_split_above = 0;    // test hook: pretend waves with more blocks than this do not fit
 };
 
@@ -178,9 +177,10 @@ extern "C" int fcx_create(int device, fcx_ctx** out) {
     if (const char* s = getenv("FCX_WAVE_PAIRS")) ctx->max_wave_pairs = (uint32_t)atoi(s);
     if (const char* s = getenv("FCX_LANES")) ctx->n_lanes = std::max(1, atoi(s));
     if (const char* s = getenv("FCX_PROFILE")) ctx->profile = atoi(s) != 0;
-    if (const char* s = getenv("FCX_DP_STAGED")) ctx->dp_staged = atoi(s) != 0;
-    if (const char* s = getenv("FCX_DP_HALF")) ctx->dp_half = atoi(s) != 0;
+    if (const char* s = getenv("FCX_DP_VARIANT")) ctx->dp_variant = atoi(s);
+#ifndef FCX_EMU
     cudaFuncSetAttribute(k_dp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+#endif
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (!getenv("FCX_WAVE_BLOCKS")) ctx->max_wave_blocks = (uint32_t)(ctx->sm_count * CNS_CTAS_PER_SM * CNS_WARPS);
     {   // never plan beyond what the device can actually give
@@ -232,8 +232,7 @@ extern "C" int fcx_set_option(fcx_ctx* ctx, const char* name, double value) {
     else if (n == "arena_gb") ctx->arena_budget = (size_t)(value * (double)((size_t)1 << 30));
     else if (n == "max_wave_blocks") ctx->max_wave_blocks = (uint32_t)value;
     else if (n == "min_wave_blocks") ctx->min_wave_blocks = (uint32_t)value;
-    else if (n == "dp_staged") ctx->dp_staged = value != 0;
-    else if (n == "dp_half") ctx->dp_half = value != 0;
+    else if (n == "dp_variant") { if (value != 1 && value != 2 && value != 3) { ctx->err = "dp_variant must be 1, 2 or 3"; return 1; } ctx->dp_variant = (int)value; }
     else if (n == "debug_split_above") ctx->debug_split_above = (uint32_t)value;
     else if (n == "lanes") ctx->active_lanes = value <= 0 ? 0 : std::min((int)value, (int)ctx->lanes.size());
     else { ctx->err = "unknown option: " + n; return 1; }
@@ -273,7 +272,7 @@ extern "C" int fcx_pool_upload(fcx_ctx* ctx, const char* bases, const uint64_t* 
     CK(cudaMemsetAsync((char*)ctx->d_pool.p + w * 4, 0, 16, ctx->stream));
     if (w > 0) {
         uint64_t nb = (w + 255) / 256;
-        k_pack<<<(unsigned)nb, 256, 0, ctx->stream>>>(ctx->d_ascii.as<uint8_t>(), ctx->d_aoff.as<uint64_t>(),
+        FCX_LAUNCH(k_pack, (unsigned)nb, 256, 0, ctx->stream, ctx->d_ascii.as<uint8_t>(), ctx->d_aoff.as<uint64_t>(),
                                                       ctx->d_woff.as<uint64_t>(), ctx->d_len.as<int32_t>(), n_reads, w,
                                                       ctx->d_pool.as<uint32_t>(), ctx->d_dirty.as<int>());
         CK(cudaGetLastError());
@@ -359,7 +358,7 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
     // ---- index
     CKL(cudaEventRecord(L.ev[0], st));
     CKL(cudaMemsetAsync(L.d_ktab.p, 0, (size_t)nb * KTAB * 4, st));
-    k_index<<<nb, 256, 0, st>>>(L.d_blocks.as<BlockDesc>(), pool, L.d_ktab.as<uint32_t>(), L.d_kpos.as<uint32_t>());
+    FCX_LAUNCH(k_index, nb, 256, 0, st, L.d_blocks.as<BlockDesc>(), pool, L.d_ktab.as<uint32_t>(), L.d_kpos.as<uint32_t>());
     CKL(cudaGetLastError());
     CKL(cudaEventRecord(L.ev[1], st));
     L.counters[FCX_C_KERNEL_LAUNCHES] += 1;
@@ -371,7 +370,7 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
         const unsigned per_sm = (unsigned)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / std::max<size_t>(rsmem, 1)));
         const unsigned rgrid = std::min<unsigned>((np + RANGE_WARPS - 1) / RANGE_WARPS, (unsigned)ctx->sm_count * per_sm);
         CKR(L.d_rlist.reserve((size_t)rgrid * RANGE_WARPS * RANGE_LIST_CAP * sizeof(int2)));
-        k_range<<<rgrid, RANGE_WARPS * 32, rsmem, st>>>(
+        FCX_LAUNCH(k_range, rgrid, RANGE_WARPS * 32, rsmem, st, 
             L.d_blocks.as<BlockDesc>(), L.d_pairs.as<PairDesc>(), np, pool, L.d_ktab.as<uint32_t>(),
             L.d_kpos.as<uint32_t>(), L.d_rlist.as<int2>(), bins, L.d_ranges.as<PairRange>());
         CKL(cudaGetLastError());
@@ -409,47 +408,32 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
     // ---- DP
     CKL(cudaEventRecord(L.ev[3], st));
     if (np) {
-        if (ctx->dp_half && !ctx->dp_staged) {
-            // two pairs per warp, pairs ordered by span (counting sort, 64-base buckets) so that the
-            // halves of a warp and the warps of a CTA carry similar work
-            std::vector<uint32_t> ord; ord.reserve(dp_pairs);
+        if (ctx->dp_variant == 3) {
+            // default: one warp per pair, diagonals pinned to lanes, V in registers (fcx_dp.cuh)
+            FCX_LAUNCH(k_dp3, (np + DP3_WARPS - 1) / DP3_WARPS, DP3_WARPS * 32, 0, st,
+                       L.d_blocks.as<BlockDesc>(), L.d_pairs.as<PairDesc>(), L.d_ranges.as<PairRange>(),
+                       L.d_allocs.as<PairAlloc>(), np, pool, L.d_trace.as<uint32_t>(), 1.0 - min_idt,
+                       L.d_aln.as<PairAln>());
+        } else {
+            // round-1 kernels kept for A/B measurement: shared-memory V ring, lanes re-mapped to the
+            // band every step; dp_variant 2 stages the spans through TMA when they fit
+            const int stage_words = (int)(((max_span + 15) / 16 + 1 + 8 + 3) & ~3u);
+            const size_t smem_staged = (size_t)DP_WARPS * ((size_t)VRING * 4 + (size_t)stage_words * 8 + 16);
+            const bool staged = ctx->dp_variant == 2 && smem_staged <= 100 * 1024;
+#ifndef FCX_EMU
+            if (staged) {
+                FCX_LAUNCH(k_dp<true>, (np + DP_WARPS - 1) / DP_WARPS, DP_WARPS * 32, smem_staged, st,
+                           L.d_blocks.as<BlockDesc>(), L.d_pairs.as<PairDesc>(), L.d_ranges.as<PairRange>(),
+                           L.d_allocs.as<PairAlloc>(), np, pool, L.d_trace.as<uint32_t>(), 1.0 - min_idt, stage_words,
+                           L.d_aln.as<PairAln>());
+            } else
+#endif
             {
-                const uint32_t NB = 200000 / 64 + 2;
-                std::vector<uint32_t> cnt(NB + 1, 0);
-                for (uint32_t pp = 0; pp < np; pp++) if (hr[pp].pass) cnt[NB - 1 - (uint32_t)((hr[pp].e1 - hr[pp].s1 + hr[pp].e2 - hr[pp].s2) / 64)]++;
-                uint32_t run = 0;
-                for (uint32_t b = 0; b <= NB; b++) { uint32_t c = cnt[b]; cnt[b] = run; run += c; }
-                ord.resize(dp_pairs);
-                for (uint32_t pp = 0; pp < np; pp++) if (hr[pp].pass) ord[cnt[NB - 1 - (uint32_t)((hr[pp].e1 - hr[pp].s1 + hr[pp].e2 - hr[pp].s2) / 64)]++] = pp;
+                FCX_LAUNCH(k_dp<false>, (np + DP_WARPS - 1) / DP_WARPS, DP_WARPS * 32, (size_t)DP_WARPS * VRING * 4, st,
+                           L.d_blocks.as<BlockDesc>(), L.d_pairs.as<PairDesc>(), L.d_ranges.as<PairRange>(),
+                           L.d_allocs.as<PairAlloc>(), np, pool, L.d_trace.as<uint32_t>(), 1.0 - min_idt, 0,
+                           L.d_aln.as<PairAln>());
             }
-            CKR(L.d_order.reserve(std::max<size_t>(1, ord.size()) * 4));
-            CKL(cudaMemcpyAsync(L.d_order.p, ord.data(), ord.size() * 4, cudaMemcpyHostToDevice, st));
-            CKL(cudaMemsetAsync(L.d_aln.p, 0, (size_t)np * sizeof(PairAln), st));     // pairs that failed the filters
-            const uint32_t n_dp = (uint32_t)ord.size();
-            if (n_dp) {
-                const uint32_t per_cta = DP2_WARPS * 2;
-                k_dp2<<<(n_dp + per_cta - 1) / per_cta, DP2_WARPS * 32, 0, st>>>(
-                    L.d_blocks.as<BlockDesc>(), L.d_pairs.as<PairDesc>(), L.d_ranges.as<PairRange>(),
-                    L.d_allocs.as<PairAlloc>(), L.d_order.as<uint32_t>(), n_dp, pool, L.d_trace.as<uint32_t>(),
-                    1.0 - min_idt, L.d_aln.as<PairAln>());
-            }
-            // (the pageable-source cudaMemcpyAsync above has staged `ord` before returning)
-        } else {
-        // staged variant: spans copied to shared memory by TMA when they fit the per-CTA budget
-        const int stage_words = (int)(((max_span + 15) / 16 + 1 + 8 + 3) & ~3u);
-        const size_t smem_staged = (size_t)DP_WARPS * ((size_t)VRING * 4 + (size_t)stage_words * 8 + 16);
-        const bool staged = ctx->dp_staged && smem_staged <= 100 * 1024;
-        if (staged) {
-            k_dp<true><<<(np + DP_WARPS - 1) / DP_WARPS, DP_WARPS * 32, smem_staged, st>>>(
-                L.d_blocks.as<BlockDesc>(), L.d_pairs.as<PairDesc>(), L.d_ranges.as<PairRange>(),
-                L.d_allocs.as<PairAlloc>(), np, pool, L.d_trace.as<uint32_t>(), 1.0 - min_idt, stage_words,
-                L.d_aln.as<PairAln>());
-        } else {
-            k_dp<false><<<(np + DP_WARPS - 1) / DP_WARPS, DP_WARPS * 32, (size_t)DP_WARPS * VRING * 4, st>>>(
-                L.d_blocks.as<BlockDesc>(), L.d_pairs.as<PairDesc>(), L.d_ranges.as<PairRange>(),
-                L.d_allocs.as<PairAlloc>(), np, pool, L.d_trace.as<uint32_t>(), 1.0 - min_idt, 0,
-                L.d_aln.as<PairAln>());
-        }
         }
         CKL(cudaGetLastError());
         L.counters[FCX_C_KERNEL_LAUNCHES] += 1;
@@ -458,11 +442,11 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
     // ---- traceback + transpose
     if (np) {
         const uint64_t n16 = (xam_n + 3) / 4 + 1;
-        k_fill32<<<(unsigned)std::min<uint64_t>((n16 + 255) / 256, (uint64_t)ctx->sm_count * 16), 256, 0, st>>>(
+        FCX_LAUNCH(k_fill32, (unsigned)std::min<uint64_t>((n16 + 255) / 256, (uint64_t)ctx->sm_count * 16), 256, 0, st, 
             L.d_ent.as<uint4>(), n16, ENT_PLAIN);
         CKL(cudaGetLastError());
         L.counters[FCX_C_KERNEL_LAUNCHES] += 1;
-        k_traceback<<<(np + 127) / 128, 128, 0, st>>>(
+        FCX_LAUNCH(k_traceback, (np + 127) / 128, 128, 0, st, 
             L.d_blocks.as<BlockDesc>(), L.d_pairs.as<PairDesc>(), L.d_ranges.as<PairRange>(),
             L.d_allocs.as<PairAlloc>(), np, pool, L.d_trace.as<uint32_t>(), L.d_path.as<uint32_t>(),
             L.d_xam.as<uint32_t>(), L.d_ent.as<uint32_t>(), L.d_aln.as<PairAln>());
@@ -470,7 +454,7 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
         L.counters[FCX_C_KERNEL_LAUNCHES] += 1;
     }
     if (tiles) {
-        k_transpose<<<(unsigned)((tiles + TR_WARPS - 1) / TR_WARPS), TR_WARPS * 32, 0, st>>>(
+        FCX_LAUNCH(k_transpose, (unsigned)((tiles + TR_WARPS - 1) / TR_WARPS), TR_WARPS * 32, 0, st, 
             L.d_blocks.as<BlockDesc>(), nb, (uint32_t)tiles, L.d_ranges.as<PairRange>(),
             L.d_allocs.as<PairAlloc>(), L.d_aln.as<PairAln>(), L.d_ent.as<uint32_t>(), L.d_M.as<uint32_t>());
         CKL(cudaGetLastError());
@@ -483,7 +467,7 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
     CKL(cudaStreamWaitEvent(sh, L.ev[5], 0));
     {
         auto kfn = ctx->profile ? k_consensus<true> : k_consensus<false>;
-        kfn<<<cns_grid, CNS_WARPS * 32, 0, sh>>>(
+        FCX_LAUNCH(kfn, cns_grid, CNS_WARPS * 32, 0, sh, 
             L.d_blocks.as<BlockDesc>(), nb, L.d_pairs.as<PairDesc>(), L.d_ranges.as<PairRange>(),
             L.d_allocs.as<PairAlloc>(), L.d_aln.as<PairAln>(), pool, L.d_xam.as<uint32_t>(),
             L.d_ent.as<uint32_t>(), L.d_M.as<uint32_t>(), L.d_recs.as<CnsRec>(), L.d_lvl.as<int32_t>(),
@@ -734,12 +718,12 @@ extern "C" int fcx_internal_align(fcx_ctx* ctx, const char* q, int q_len, const 
     CK(ctx->d_str1.reserve(2 * ((size_t)q_len + t_len + 2)));
     CK(cudaMemsetAsync(ctx->d_path1.p, 0, (size_t)(max_d / 32 + 2) * 4, st));
     const uint32_t* pool = ctx->d_pool.as<uint32_t>();
-    k_align1<<<1, 32, 0, st>>>(pool, ctx->h_woff[0], ctx->h_woff[1], q_len, t_len, band_tolerance,
+    FCX_LAUNCH(k_align1, 1, 32, 0, st, pool, ctx->h_woff[0], ctx->h_woff[1], q_len, t_len, band_tolerance,
                                ctx->d_trace1.as<uint32_t>(), rec_words, ctx->d_aln1.as<PairAln>());
     CK(cudaGetLastError());
     char* dq = ctx->d_str1.as<char>(); char* dt = dq + (size_t)q_len + t_len + 2;
     if (get_aln_str > 0) {
-        k_align1_tb<<<1, 1, 0, st>>>(pool, ctx->h_woff[0], ctx->h_woff[1], q_len, t_len, ctx->d_trace1.as<uint32_t>(),
+        FCX_LAUNCH(k_align1_tb, 1, 1, 0, st, pool, ctx->h_woff[0], ctx->h_woff[1], q_len, t_len, ctx->d_trace1.as<uint32_t>(),
                                      rec_words, ctx->d_path1.as<uint32_t>(), ctx->d_aln1.as<PairAln>(), dq, dt);
         CK(cudaGetLastError());
     }

@@ -14,8 +14,22 @@
 // Every kernel reproduces the reference's integer/double semantics exactly, including the quirks
 // listed in SURVEY.md 8(a)-notes; see DESIGN.md for the data layout.
 #pragma once
+#include <climits>
 #include <cstdint>
+#include <type_traits>
 #include <cuda_runtime.h>
+
+// Launch and dynamic-shared-memory spellings.  FCX_EMU is defined only by tests/emu (a SIMT
+// emulator used to check kernel logic on machines without a GPU); the product is built by nvcc.
+#ifdef FCX_EMU
+#define FCX_LAUNCH(kern, grid, block, smem, stream, ...) \
+    emu::launch(emu::Dim3((unsigned)(grid)), emu::Dim3((unsigned)(block)), (size_t)(smem), [&]() { kern(__VA_ARGS__); })
+#define FCX_DYN_SHARED(type, name) type* name = reinterpret_cast<type*>(emu::g_cta->dyn_smem)
+#else
+#define FCX_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define FCX_DYN_SHARED(type, name) extern __shared__ __align__(16) unsigned char name##_raw_[]; \
+    type* name = reinterpret_cast<type*>(name##_raw_)
+#endif
 
 namespace fcx {
 
@@ -85,7 +99,11 @@ __device__ __forceinline__ int base_at(const uint32_t* __restrict__ w, int pos) 
     return (int)((__ldg(w + (pos >> 4)) >> ((pos & 15) << 1)) & 3u);
 }
 __device__ __forceinline__ unsigned lanemask_lt() {
+#ifdef FCX_EMU
+    return (1u << (threadIdx.x & 31)) - 1u;
+#else
     unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m;
+#endif
 }
 
 // ------------------------------------------------------------------------------ k_pack
@@ -318,7 +336,7 @@ k_range(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs
         const uint32_t* __restrict__ pool, const uint32_t* __restrict__ ktab,
         const uint32_t* __restrict__ kpos_arena, int2* __restrict__ list_scratch, int bins,
         PairRange* __restrict__ out) {
-    extern __shared__ int s_hist_all[];
+    FCX_DYN_SHARED(int, s_hist_all);
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     int* hist = s_hist_all + wib * bins;      // bins >= (max read len + max seed len) / 48 + 2 for this wave
     const uint32_t gw = blockIdx.x * RANGE_WARPS + wib, nw = gridDim.x * RANGE_WARPS;
@@ -498,6 +516,7 @@ __device__ __forceinline__ DpCell dp_cell(const int* V, int d, int k, int min_k,
 }
 
 // TMA (1-D bulk async copy, cp.async.bulk -> SASS UBLKCP) + mbarrier helpers for the staged variant
+#ifndef FCX_EMU
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // init visible to the async (TMA) proxy
@@ -519,6 +538,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
     }
 }
 
+#else   // the SIMT emulator has no async proxy: the staged variant is never launched there
+__device__ __forceinline__ void mbar_init(uint64_t*, uint32_t) {}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t*, uint32_t) {}
+__device__ __forceinline__ void tma_load_1d(void*, const void*, uint32_t, uint64_t*) {}
+__device__ __forceinline__ void mbar_wait(uint64_t*, uint32_t) {}
+#endif
+
 // STAGED = true: the two packed spans of the pair are copied into shared memory by one TMA bulk
 // copy each (dynamic shared memory: per warp V ring + 2 x stage_words words + an mbarrier) and the
 // snakes read shared memory; STAGED = false reads them through the read-only L1 path.
@@ -528,7 +554,7 @@ k_dp(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs,
      const PairRange* __restrict__ ranges, const PairAlloc* __restrict__ allocs, uint32_t n_pairs,
      const uint32_t* __restrict__ pool, uint32_t* __restrict__ trace_arena, double max_diff,
      int stage_words, PairAln* __restrict__ out) {
-    extern __shared__ __align__(16) unsigned char s_dyn[];
+    FCX_DYN_SHARED(unsigned char, s_dyn);
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t p = blockIdx.x * DP_WARPS + wib;
     if (p >= n_pairs) return;
@@ -561,7 +587,9 @@ k_dp(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs,
         q = sq - wq0; t = st - wt0;
     }
     int max_d = (int)(0.3 * (q_len + t_len));                 // DW_banded.c:149
+#ifndef FCX_EMU
     asm volatile("" : "+r"(max_d));     // keep the FP64 conversion out of the d loop (ptxas rematerialises it)
+#endif
     const int band_size = BAND_TOL * 2;                        // :151
     const PairAlloc al = allocs[p];
     uint32_t* trace = trace_arena + al.trace_off * TRACE_REC_WORDS;
@@ -684,145 +712,11 @@ k_dp(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs,
     if (lane == 0) out[p] = res;
 }
 
-// ------------------------------------------------------------------------------ k_dp2
-// Same forward pass, two pairs per warp: each half-warp (16 lanes) owns one pair and walks its band
-// in rounds of 16 cells (the band holds ~29 cells on average, so a full warp per pair idles half its
-// lanes on every second pass).  Pairs come from `order[]`, sorted by span on the host, so the two
-// halves of a warp (and the warps of a CTA) finish at about the same time.  Per-half state lives in
-// registers replicated across the half; collectives are full-warp ballots split by half, or
-// half-masked reductions.  Trace format is identical to k_dp (round r = half-word r of the record's
-// ballot words), so k_traceback is shared.
-constexpr int DP2_WARPS = 4;
-constexpr int DP2_RREG = 4;        // rounds whose x+y stays in registers for the band update (<= 64 cells)
+}  // namespace fcx
 
-__global__ void __launch_bounds__(DP2_WARPS * 32)
-k_dp2(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs,
-      const PairRange* __restrict__ ranges, const PairAlloc* __restrict__ allocs,
-      const uint32_t* __restrict__ order, uint32_t n_dp,
-      const uint32_t* __restrict__ pool, uint32_t* __restrict__ trace_arena, double max_diff,
-      PairAln* __restrict__ out) {
-    __shared__ int s_V[DP2_WARPS][2][VRING];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int h = lane >> 4, hl = lane & 15;
-    const unsigned hmask = 0xffffu << (16 * h);
-    const uint32_t slot = (blockIdx.x * DP2_WARPS + wib) * 2 + h;
-    const bool valid = slot < n_dp;
-    const uint32_t p = valid ? order[slot] : 0u;
-    PairAln res; res.aligned = res.dist = res.aln_size = res.q_e = res.t_e = res.k_end = 0;
-    res.accepted = res.t_cnt = res.n_tags = res.cells = 0;
-    const uint32_t* q = pool; const uint32_t* t = pool;
-    int qs = 0, ts = 0, q_len = 0, t_len = 0, max_d = 0, trace_cap = 0;
-    uint32_t* trace = trace_arena;
-    if (valid) {
-        const PairRange rg = ranges[p];
-        const PairDesc pd = pairs[p];
-        q = pool + pd.read_woff; t = pool + blocks[pd.block].seed_woff;
-        qs = rg.s1; ts = rg.s2; q_len = rg.e1 - rg.s1; t_len = rg.e2 - rg.s2;
-        max_d = (int)(0.3 * (q_len + t_len));                  // DW_banded.c:149
-        const PairAlloc al = allocs[p];
-        trace = trace_arena + al.trace_off * TRACE_REC_WORDS;
-        trace_cap = (int)al.trace_cap;
-    }
-    asm volatile("" : "+r"(max_d));
-    const int band_size = BAND_TOL * 2;
-    int* V = s_V[wib][h];
+#include "fcx_dp.cuh"
 
-    int best_m = -1, min_k = 0, max_k = 0, cells = 0;
-    bool aligned = false; int end_d = 0, end_k = 0, end_x = 0, end_y = 0;
-    // ---- d = 0: the single cell k = 0 of each pair
-    if (max_d > 0) {
-        int x = 0, y = 0;
-        snake(q, t, qs, ts, q_len, t_len, x, y);
-        if (hl == 0 && trace_cap > 0) { trace[0] = 0u; trace[1] = 1u; }
-        cells = 1;
-        if (x >= q_len || y >= t_len) { aligned = true; end_x = x; end_y = y; }
-        else { if (hl == 0) V[0] = x; best_m = x + y; min_k = -1; max_k = 1; }
-    }
-    __syncwarp();
-    bool failed = false;
-    for (int d = 1;; d++) {
-        if (!aligned && !failed && (d >= max_d || max_k - min_k > band_size)) failed = true;   // :183-186
-        const bool live = valid && !aligned && !failed;
-        if (!__any_sync(FULL, live)) break;
-        const int ncell = live ? ((max_k - min_k) >> 1) + 1 : 0;
-        const int R = __reduce_max_sync(FULL, (ncell + 15) >> 4);
-        uint32_t* rec = trace + (size_t)d * TRACE_REC_WORDS;
-        const bool rec_ok = live && d < trace_cap;
-        if (hl == 0 && rec_ok) rec[0] = (uint32_t)min_k;
-        uint16_t* rec16 = reinterpret_cast<uint16_t*>(rec + 1);
-        bool fin_found = false;
-        int ureg[DP2_RREG], umax = INT_MIN;
-        // one round = 16 consecutive cells of each half
-        auto round = [&](const int r) -> int {
-            const int ci = hl + 16 * r;
-            const int k = min_k + 2 * ci;
-            const bool act = live && !fin_found && ci < ncell;
-            DpCell c = dp_pick(V, k, min_k, max_k, act);
-            int n = snake16(q, t, qs, ts, q_len, t_len, act, c.x, c.y);
-            while (__ballot_sync(FULL, n == 16)) {                      // long snakes: rare
-                if (n == 16) n = snake16(q, t, qs, ts, q_len, t_len, true, c.x, c.y);
-            }
-            const unsigned upb = __ballot_sync(FULL, c.up);
-            if (hl == 0 && rec_ok && 16 * r < ncell) rec16[r] = (uint16_t)(upb >> (16 * h));
-            const unsigned finb = __ballot_sync(FULL, act && (c.x >= q_len || c.y >= t_len));     // :220
-            const unsigned myfin = (finb >> (16 * h)) & 0xffffu;
-            const int fl = myfin ? __ffs(myfin) - 1 : 0;
-            const int fx = __shfl_sync(FULL, c.x, (h << 4) + fl), fy = __shfl_sync(FULL, c.y, (h << 4) + fl);
-            if (myfin) {                                                  // first k in ascending order wins
-                aligned = true; end_d = d; end_k = min_k + 2 * (16 * r + fl); end_x = fx; end_y = fy;
-                cells += 16 * r + fl + 1; fin_found = true;
-            }
-            if (act) V[k & (VRING - 1)] = c.x;
-            return act ? c.x + c.y : INT_MIN;
-        };
-#pragma unroll
-        for (int r = 0; r < DP2_RREG; r++) {
-            ureg[r] = INT_MIN;
-            if (r < R) { ureg[r] = round(r); umax = max(umax, ureg[r]); }
-        }
-        for (int r = DP2_RREG; r < R; r++) umax = max(umax, round(r));    // bands wider than 64 cells: rare
-        const int bm = __reduce_max_sync(hmask, umax);
-        const bool go_on = live && !aligned;
-        if (go_on) { cells += ncell; best_m = max(best_m, bm); }
-        __syncwarp();
-        // band update, :227-243
-        const int thr = best_m - BAND_TOL;
-        int nmin = INT_MAX, nmax = INT_MIN;
-#pragma unroll
-        for (int r = 0; r < DP2_RREG; r++) {
-            if (r < R) {
-                const unsigned okb = __ballot_sync(FULL, go_on && ureg[r] >= thr);
-                const unsigned my = (okb >> (16 * h)) & 0xffffu;
-                if (my) {
-                    if (nmin == INT_MAX) nmin = min_k + 2 * (16 * r + __ffs(my) - 1);
-                    nmax = min_k + 2 * (16 * r + 31 - __clz(my));
-                }
-            }
-        }
-        for (int r = DP2_RREG; r < R; r++) {
-            const int ci = hl + 16 * r, k = min_k + 2 * ci;
-            bool ok = false;
-            if (go_on && ci < ncell) { const int x = V[k & (VRING - 1)]; ok = (2 * x - k) >= thr; }
-            const unsigned okb = __ballot_sync(FULL, ok);
-            const unsigned my = (okb >> (16 * h)) & 0xffffu;
-            if (my) {
-                if (nmin == INT_MAX) nmin = min_k + 2 * (16 * r + __ffs(my) - 1);
-                nmax = min_k + 2 * (16 * r + 31 - __clz(my));
-            }
-        }
-        if (go_on) { max_k = nmax + 1; min_k = nmin - 1; }
-        __syncwarp();
-    }
-    if (aligned) {
-        res.aligned = 1; res.dist = end_d; res.q_e = end_x; res.t_e = end_y; res.k_end = end_k;
-        res.aln_size = (end_x + end_y + end_d) / 2;
-        res.accepted = (res.aln_size > 500 &&
-                        ((double)res.dist / (double)res.aln_size) < max_diff) ? 1 : 0;   // falcon.c:629
-        if (res.accepted && end_d >= trace_cap) res.accepted = -1;
-    }
-    res.cells = cells;
-    if (valid && hl == 0) out[p] = res;
-}
+namespace fcx {
 
 // ------------------------------------------------------------------------------ k_traceback
 // One thread per accepted pair.  (1) walk the trace records backwards collecting the direction

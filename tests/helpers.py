@@ -44,3 +44,33 @@ def run_cli(argv, stdin_bytes, engine, python_parser=False):
     out = io.StringIO()
     consensus.run(args, stdin=io.BytesIO(stdin_bytes), stdout=out, engine=engine)
     return out.getvalue().encode()
+
+
+# ---------------------------------------------------------------------------------------------
+# SIMT-emulator build of the CUDA sources (tests/emu): lets the kernel logic be checked against the
+# oracle on a machine without a GPU.  Test infrastructure only -- falcon_b200.binding never loads it.
+EMU_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu")
+EMU_SO = os.path.join(EMU_DIR, "_build", "libfalcon_b200_emu.so")
+
+
+def build_emu():
+    import subprocess
+    subprocess.run(["make", "-s", "-C", EMU_DIR], check=True)
+    return EMU_SO
+
+
+def emu_engine():
+    """A falcon_b200.binding.Engine whose library handle is the emulator build."""
+    import ctypes as C
+    from falcon_b200 import binding
+
+    class EmuEngine(binding.Engine):
+        def __init__(self):
+            self._lib = binding.load_library(build_emu())
+            h = C.c_void_p()
+            if self._lib.fcx_create(0, C.byref(h)) != 0:
+                raise binding.EngineError("fcx_create (emu): %s" % self._lib.fcx_last_error(None).decode())
+            self._h = h
+            self.n_reads = 0
+
+    return EmuEngine()

@@ -1,0 +1,78 @@
+"""CPU: the CUDA kernel SOURCES compiled against the SIMT emulator (tests/emu) and run through the
+same C ABI as on the GPU, checked against the oracle bit for bit.  This is how kernel logic is
+validated on the authoring container (no GPU); the `gpu`-marked tests repeat it on the B200.
+The emulator library is test infrastructure: falcon_b200.binding never loads it."""
+import numpy as np
+import pytest
+
+from falcon_b200 import synth
+from helpers import emu_engine
+
+import test_gpu_parity as G
+
+
+@pytest.fixture(scope="module")
+def emu():
+    return emu_engine()
+
+
+@pytest.mark.parametrize("params", [
+    dict(genome_size=30000, read_len=2500, coverage=20, seed=1, n_blocks=3),
+    dict(genome_size=30000, read_len=3000, coverage=14, seed=2, n_blocks=3, len_sigma=0.4),
+    dict(genome_size=60000, read_len=8000, coverage=12, seed=3, n_blocks=2),
+    dict(genome_size=30000, read_len=3000, coverage=15, seed=5, n_blocks=3, p_ins=0.05, p_del=0.05, p_sub=0.05),
+])
+def test_stage_parity_with_oracle(emu, oracle, params):
+    G._check_set(emu, oracle, synth.make_set(**params), min_cov=4)
+
+
+def test_min_cov_and_idt_variants(emu, oracle):
+    S = synth.make_set(30000, 3000, 16, seed=6, n_blocks=2)
+    for min_cov, min_idt in ((0, 0.70), (1, 0.80), (200, 0.70)):
+        G._check_set(emu, oracle, S, min_cov, min_idt)
+
+
+def test_edge_blocks(emu, oracle):
+    G.test_edge_blocks(emu, oracle)
+
+
+def test_low_complexity_match_list_overflow(emu, oracle):
+    G.test_low_complexity_match_list_overflow(emu, oracle)
+
+
+def test_long_insertions_take_the_generic_consensus_path(emu, oracle):
+    G.test_long_insertions_take_the_generic_consensus_path(emu, oracle)
+
+
+def test_unaligned_and_rejected_pairs(emu, oracle):
+    """includes a 200-base insertion: the DP band passes 64 cells (wide mode of k_dp3) and then
+    exceeds the band limit"""
+    G.test_unaligned_and_rejected_pairs(emu, oracle)
+
+
+def test_wide_bands_stay_exact(emu, oracle):
+    """Low-complexity pairs (shared homopolymer / dinucleotide runs) keep many diagonals within the
+    band tolerance: bands of 65..151 cells run in k_dp3's shared-memory wide mode."""
+    rng = np.random.default_rng(77)
+    g = synth.random_codes(5000, rng)
+    g[1500:1700] = 1
+    g[3000:3300] = np.tile([0, 2], 150)
+    seed = synth.codes_to_bytes(g)
+    reads = [synth.codes_to_bytes(synth.add_errors(g, rng, 0.05, 0.03, 0.01)) for _ in range(6)]
+    seqs = [seed, seed] + reads
+    emu.upload_pool(seqs)
+    got = emu.consensus_blocks([list(range(len(seqs)))], 2, 0.70)[0]
+    info = emu.pair_info()
+    want, oinfo = oracle.generate_consensus(seqs, 2, 0.70, want_info=True)
+    for j, (g_, o_) in enumerate(zip(info, oinfo[1:])):
+        assert (g_.aligned, g_.accepted, g_.trace_cells) == (o_.aligned, o_.accepted, o_.trace_cells), j
+        if o_.aligned:
+            assert (g_.dist, g_.aln_size, g_.q_e, g_.t_e) == (o_.dist, o_.aln_size, o_.q_e, o_.t_e), j
+    assert got == want
+
+
+@pytest.mark.parametrize("variant", [1])
+def test_round1_dp_kernel_still_agrees(oracle, variant):
+    e = emu_engine()
+    e.set_option("dp_variant", variant)
+    G._check_set(e, oracle, synth.make_set(30000, 2500, 14, seed=9, n_blocks=2), min_cov=3)
