@@ -6,22 +6,33 @@
         --master-port P bench.py --gpus N --steps K --warmup W
 
 A "step" is one pass of the whole hot path (k-mer range -> banded O(ND) DP -> traceback ->
-alignment-graph consensus) over this rank's seed blocks of the synthetic workload:
-E. coli-like uniform random genome, 50x coverage of 15 kb reads, 15 % error (ins 9 / del 4.5 /
-sub 1.5), blocks built from ground truth.  Weak scaling: every rank owns an equal
-slice of a genome that grows with N; there is no data-path collective.
+alignment-graph consensus) over ONE synthetic data set: uniform random genome, 50x coverage of
+15 kb reads, 15 % error (ins 9 / del 4.5 / sub 1.5), seed blocks built from ground truth
+(SURVEY.md 8(d)).
 
-`value`  : pairs/s with the read pool already resident in HBM (timed with CUDA events on the
-           engine's stream, max over ranks).
-`e2e`    : the same metric through the public batched C-ABI call with HOST buffers: every step
-           uploads the read pool from pinned host memory and reads the consensus back.
+  N = 1   BASELINE config 2: E. coli-like 4.6 Mb (15.3 k seed blocks, ~1.45 M pairs per step).
+  N >= 2  one "D. mel-like slice" (8 x 4.6 Mb = 36.8 Mb, ~11.6 M pairs per step) SHARDED over the
+          N GPUs -- strong scaling: every rank generates and packs 1/N of the reads, the 2-bit
+          packed read store is completed on every GPU with one NCCL broadcast per part
+          (SURVEY.md 8(e)), seed blocks are cut into N cost-balanced contiguous slices
+          (falcon_b200/shard.py), results are gathered to rank 0 and merged in seed order
+          (the ordering contract of falcon_kit/mains/consensus.py:274).
+
+`value`  : pairs/s with the read store already resident in HBM (CUDA events on the engine's stream,
+           max over ranks).
+`e2e`    : the same through the public C-ABI calls with HOST buffers: every step uploads the read
+           bytes from pinned host memory, (N > 1) broadcasts the packed parts, runs, and brings
+           the consensus of all blocks to rank 0's host memory in seed order.
 `roofline`: dominant kernel, algorithmic bytes / its CUDA-event time.
-`cpu_baseline`: the reference's own C code (oracle/_ref/falcon.so, or the oracle port if that is
-           absent) on the host cores, on a bounded sample of the same blocks.
+`cpu_baseline`: the reference's own C code (oracle/_ref/falcon.so; the oracle port if that is
+           absent) on the host cores this process may use, on a bounded sample of the same blocks.
+PARITY GATE: before any number is printed, the consensus of every CPU-sampled block is compared
+with the GPU result of the same block; a difference aborts the run.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import multiprocessing as mp
 import os
@@ -37,33 +48,37 @@ import numpy as np  # noqa: E402
 
 METRIC = "aligned read-pairs/sec fc_consensus"
 UNIT = "pairs/s"
+ECOLI = 4_600_000
 
 
-# ------------------------------------------------------------------------------- workload
-def build_workload(args, rank):
-    from falcon_b200 import synth
-    n_reads = int(round(args.genome * args.cov / args.read_len))
-    stride = max(1, n_reads // args.blocks) if args.blocks and args.blocks < n_reads else 1
-    S = synth.make_set(args.genome, args.read_len, args.cov, seed=args.seed + 1000 * rank,
-                       n_blocks=args.blocks if args.blocks else None, max_n_read=args.max_n_read,
-                       block_stride=stride)
-    return S
+# ------------------------------------------------------------------------------- host facts
+def usable_cores() -> int:
+    """Cores this process may really use: affinity mask capped by the cgroup CPU quota."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            q, p = f.read().split()
+            if q != "max":
+                n = min(n, max(1, int(float(q) / float(p))))
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            p = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, q // p))
+        except Exception:
+            pass
+    return max(1, n)
 
 
-def flatten(S, pinned=True):
-    """Pool -> (pinned uint8 buffer, uint64 offsets), blocks -> (uint32 block_off, uint32 read_ids)."""
-    from falcon_b200.binding import PinnedBuffer
-    lens = np.fromiter((len(r) for r in S.pool), dtype=np.uint64, count=len(S.pool))
-    off = np.zeros(len(S.pool) + 1, dtype=np.uint64)
-    np.cumsum(lens, out=off[1:])
-    total = int(off[-1])
-    buf = PinnedBuffer(total)
-    cat = np.frombuffer(b"".join(S.pool), dtype=np.uint8)
-    buf.array[:total] = cat
-    block_off = np.zeros(len(S.blocks) + 1, dtype=np.uint32)
-    np.cumsum([len(b) for b in S.blocks], out=block_off[1:])
-    ids = np.concatenate(S.blocks).astype(np.uint32)
-    return buf, off, block_off, ids
+def cpu_model() -> str:
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
 
 
 # ------------------------------------------------------------------------------- clocks
@@ -109,7 +124,6 @@ _W = {}
 
 
 def _ref_worker_init(so_path, kind):
-    import ctypes as C
     sys.path.insert(0, ROOT)
     if kind == "reference":
         from oracle.oracle import Ref
@@ -121,48 +135,63 @@ def _ref_worker_init(so_path, kind):
 
 def _ref_worker_run(job):
     seqs, min_cov, min_idt = job
+    t0 = time.process_time()
     cns = _W["eng"].generate_consensus(seqs, min_cov, min_idt)
-    return len(cns)
+    return hashlib.md5(cns).hexdigest(), len(cns), time.process_time() - t0
 
 
-def cpu_reference_pool(cores):
-    from oracle import oracle as orc
-    try:
-        orc.build()
-    except Exception:
-        pass
-    kind = "reference" if os.path.exists(orc.REF_SO) else "port"
-    ctx = mp.get_context("fork")
-    pool = ctx.Pool(cores, initializer=_ref_worker_init, initargs=(orc.REF_SO, kind))
-    return pool, kind
+class CpuReference:
+    """The reference's own C code on the host cores, one forked worker per core: the structure of
+    falcon_kit/mains/consensus.py:264-274 (exe_pool.imap over seed blocks)."""
+
+    def __init__(self, cores):
+        from oracle import oracle as orc
+        try:
+            orc.build()
+        except Exception:
+            pass
+        self.kind = "reference" if os.path.exists(orc.REF_SO) else "port"
+        self.cores = cores
+        self.pool = mp.get_context("fork").Pool(cores, initializer=_ref_worker_init, initargs=(orc.REF_SO, self.kind))
+
+    def run(self, jobs):
+        """-> (wall seconds, summed worker CPU seconds, [(md5, len)])"""
+        t0 = time.perf_counter()
+        res = list(self.pool.imap(_ref_worker_run, jobs, 1))
+        dt = time.perf_counter() - t0
+        return dt, sum(r[2] for r in res), [(r[0], r[1]) for r in res]
+
+    def close(self):
+        self.pool.terminate()
 
 
-def cpu_reference_time(pool, S, block_ids, min_cov, min_idt, chunksize=1):
-    jobs = [(S.block_seqs(b), min_cov, min_idt) for b in block_ids]
-    pairs = sum(len(j[0]) - 1 for j in jobs)
-    t0 = time.perf_counter()
-    list(pool.imap(_ref_worker_run, jobs, chunksize))
-    dt = time.perf_counter() - t0
-    return pairs, dt
+def sample_jobs(pool_reads, blocks, ids, min_cov, min_idt):
+    return [([pool_reads[i] for i in blocks[b]], min_cov, min_idt) for b in ids]
 
 
-# ------------------------------------------------------------------------------- main
+# ------------------------------------------------------------------------------- helpers
+class _DevArray:
+    """Zero-copy view of device memory for torch.as_tensor (CUDA array interface)."""
+
+    def __init__(self, ptr, n_words):
+        self.__cuda_array_interface__ = {"shape": (n_words,), "typestr": "<i4", "data": (ptr, False), "version": 2}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--genome", type=int, default=4_600_000)
+    ap.add_argument("--genome", type=int, default=0, help="genome size (0 = 4.6 Mb at N=1, 36.8 Mb at N>=2)")
     ap.add_argument("--read-len", type=int, default=15000)
     ap.add_argument("--cov", type=float, default=50.0)
-    ap.add_argument("--blocks", type=int, default=0,
-                    help="seed blocks per rank per step (0 = the whole set: every read is a seed, ~15.3k blocks)")
+    ap.add_argument("--blocks", type=int, default=0, help="seed blocks per step (0 = every read is a seed)")
     ap.add_argument("--max-n-read", type=int, default=200)
     ap.add_argument("--min-cov", type=int, default=4)
     ap.add_argument("--min-idt", type=float, default=0.70)
     ap.add_argument("--seed", type=int, default=20260924)
-    ap.add_argument("--cpu-sample-blocks", type=int, default=0, help="blocks in the CPU baseline sample (0 = 2 per core)")
+    ap.add_argument("--cpu-blocks-per-core", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -170,36 +199,56 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    cores = os.cpu_count() or 1
-    workload = ("synthetic E. coli-like %.1f Mb, %gx %d kb reads, 15%% error (ins 9/del 4.5/sub 1.5); %s seed blocks "
-                "per rank per step, max_n_read %d" % (args.genome / 1e6, args.cov, args.read_len // 1000,
-                                                       args.blocks or "all", args.max_n_read))
+    genome = args.genome or (ECOLI if world == 1 else 8 * ECOLI)
+    cores = usable_cores()
+    name = "E. coli-like" if genome <= 5_000_000 else "D. mel-like slice"
+    workload = ("synthetic %s %.1f Mb, %gx %d kb reads, 15%% error (ins 9/del 4.5/sub 1.5); %s seed blocks per step, "
+                "max_n_read %d; ONE data set sharded over %d GPU(s)" %
+                (name, genome / 1e6, args.cov, args.read_len // 1000, args.blocks or "all", args.max_n_read, world))
     config = {"workload": workload, "min_cov": args.min_cov, "min_idt": args.min_idt, "K": 8,
-              "parallelism": "seed-block shards, %d rank(s), no data-path collective" % world,
+              "parallelism": ("single GPU" if world == 1 else
+                              "%d ranks: packed read store completed by NCCL broadcast of each rank's part, "
+                              "cost-balanced contiguous seed-block slices, ordered gather to rank 0" % world),
               "l2": "inputs_larger_than_L2"}
+    scaling = "strong" if world > 1 else "weak"   # N=1 has nothing to scale; N>=2 share one fixed data set
+
+    from falcon_b200 import synth, shard
+    geo = synth.make_geometry(genome, args.read_len, args.cov, seed=args.seed)
+    n_reads = geo.n_reads
 
     # ---------------------------------------------------------------- reference arm
     if args.impl == "reference":
         if rank != 0:
             return 0
-        S = build_workload(args, 0)
-        nblk = args.cpu_sample_blocks or min(len(S.blocks), 2 * cores)
-        ids = list(range(nblk))
-        pool, kind = cpu_reference_pool(cores)
-        for _ in range(max(1, args.warmup)):
-            cpu_reference_time(pool, S, ids[:max(1, min(nblk, cores))] if _ == 0 else ids, args.min_cov, args.min_idt)
-        t_tot, pairs_tot = 0.0, 0
+        nblk = min(n_reads, args.cpu_blocks_per_core * cores)
+        seeds = list(range(nblk))                                   # a contiguous stretch of the genome
+        lo = 0
+        hi = int(np.searchsorted(geo.starts, geo.ends[seeds[-1]], side="left"))
+        part = synth.gen_reads(geo, lo, hi)
+        noisy = np.zeros(n_reads, dtype=np.int64)
+        noisy[lo:hi] = [len(part[2 * i]) for i in range(hi - lo)]
+        blocks, _, _ = synth.build_blocks(geo, noisy, seeds, max_n_read=args.max_n_read)
+        reads = {2 * (lo + i) + o: part[2 * i + o] for i in range(hi - lo) for o in (0, 1)}
+        jobs = sample_jobs(reads, blocks, range(len(blocks)), args.min_cov, args.min_idt)
+        pairs = sum(len(j[0]) - 1 for j in jobs)
+        cpu = CpuReference(cores)
+        cpu.run(jobs[:cores])                                       # warm the workers (msa_array init)
+        for _ in range(max(0, args.warmup - 1)):
+            cpu.run(jobs)
+        t_tot = cpu_tot = 0.0
         for _ in range(args.steps):
-            pairs, dt = cpu_reference_time(pool, S, ids, args.min_cov, args.min_idt)
-            t_tot += dt; pairs_tot += pairs
-        pool.terminate()
-        v = pairs_tot / t_tot
-        sample = "%d seed blocks (%d pairs) of the workload per step" % (nblk, pairs_tot // max(1, args.steps))
+            dt, cs, _ = cpu.run(jobs)
+            t_tot += dt; cpu_tot += cs
+        cpu.close()
+        v = pairs * args.steps / t_tot
+        sample = "%d seed blocks (%d pairs) of the workload per step, %d per core" % (len(jobs), pairs, args.cpu_blocks_per_core)
         print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
-                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+                          "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "int32",
                           "data": "synthetic", "config": config,
-                          "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+                          "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": cpu.kind, "sample": sample,
+                                           "cpu_model": cpu_model(), "os_cpu_count": os.cpu_count(),
+                                           "per_core_pairs_per_cpu_second": pairs * args.steps / cpu_tot},
                           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return 0
 
@@ -212,15 +261,9 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    from falcon_b200.binding import Engine, lib
+    from falcon_b200.binding import Engine, PinnedBuffer, lib
     import ctypes as C
-
-    S = build_workload(args, rank)
-    buf, off, block_off, ids = flatten(S)
-    n_pairs = int(S.n_pairs)
-    eng = Engine(local_rank)
-    eng.set_option("pair_info", 0)
-    L = lib()
+    dev = torch.device("cuda", local_rank)
 
     def barrier():
         torch.cuda.synchronize()
@@ -228,19 +271,96 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def allmax(x):
+    def allred(x, op):
         if world == 1:
             return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=op)
         return float(t.item())
 
-    def allsum(x):
+    # ---- this rank's part of the reads (contiguous in read order), generated and kept in pinned memory
+    cuts = [n_reads * r // world for r in range(world + 1)]
+    r0, r1 = cuts[rank], cuts[rank + 1]
+    t_gen = time.perf_counter()
+    part = synth.gen_reads(geo, r0, r1)                                   # 2 pool entries per read
+    plen = np.fromiter((len(x) for x in part), dtype=np.uint64, count=len(part))
+    poff = np.zeros(len(part) + 1, dtype=np.uint64)
+    np.cumsum(plen, out=poff[1:])
+    pbuf = PinnedBuffer(int(poff[-1]))
+    pbuf.array[:int(poff[-1])] = np.frombuffer(b"".join(part), dtype=np.uint8)
+    # lengths of all pool entries (tiny all-gather: the layout must be the same everywhere)
+    noisy = np.zeros(n_reads, dtype=np.int64)
+    noisy[r0:r1] = plen[0::2].astype(np.int64)
+    if world > 1:
+        tn = torch.from_numpy(noisy).to(dev)
+        dist.all_reduce(tn, op=dist.ReduceOp.SUM)
+        noisy = tn.cpu().numpy()
+    all_len = np.repeat(noisy.astype(np.uint64), 2)
+    all_off = np.zeros(2 * n_reads + 1, dtype=np.uint64)
+    np.cumsum(all_len, out=all_off[1:])
+    # ---- seed blocks: every read is a seed (or a strided subset); contiguous cost-balanced slices
+    stride = max(1, n_reads // args.blocks) if args.blocks and args.blocks < n_reads else 1
+    seeds_all = list(range(0, n_reads, stride))
+    if args.blocks:
+        seeds_all = seeds_all[:args.blocks]
+    slices = shard.partition(shard.block_costs([1] * len(seeds_all), [noisy[s] for s in seeds_all]), world)
+    b0, b1 = slices[rank]
+    blocks, _, _ = synth.build_blocks(geo, noisy, seeds_all[b0:b1], max_n_read=args.max_n_read)
+    block_off = np.zeros(len(blocks) + 1, dtype=np.uint32)
+    np.cumsum([len(b) for b in blocks], out=block_off[1:])
+    ids = (np.concatenate(blocks) if blocks else np.zeros(0)).astype(np.uint32)
+    n_pairs = int(sum(len(b) - 1 for b in blocks))
+    t_gen = time.perf_counter() - t_gen
+
+    eng = Engine(local_rank)
+    eng.set_option("pair_info", 0)
+    L = lib()
+    bcast_bytes = [0]
+
+    def build_store():
+        """Read store on this GPU: own part from pinned host memory, the other parts by NCCL."""
+        eng.pool_reserve(all_off)
+        eng.pool_upload_part(pbuf.ptr, poff, 2 * r0)
+        if world > 1:
+            ptr, n_words, woff = eng.pool_device()
+            view = torch.as_tensor(_DevArray(ptr, n_words), device=dev)
+            torch.cuda.synchronize()
+            for k in range(world):
+                w0, w1 = int(woff[2 * cuts[k]]), int(woff[2 * cuts[k + 1]])
+                if w1 > w0:
+                    dist.broadcast(view[w0:w1], src=k)
+            torch.cuda.synchronize()
+            bcast_bytes[0] = int(n_words) * 4
+        eng.pool_commit()
+
+    def run_blocks():
+        return eng.consensus_blocks_raw(block_off, ids, args.min_cov, args.min_idt)
+
+    def gather_to_rank0(data, off):
+        """Consensus bytes + lengths of every rank -> rank 0, merged in seed order."""
         if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+            return data, off
+        lens = np.diff(off).astype(np.int64)
+        sizes = torch.tensor([data.shape[0], lens.shape[0]], dtype=torch.int64, device=dev)
+        allsz = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(world)]
+        dist.all_gather(allsz, sizes)
+        allsz = [t.tolist() for t in allsz]
+        mx_d, mx_l = max(s[0] for s in allsz), max(s[1] for s in allsz)
+        td = torch.zeros(mx_d, dtype=torch.uint8, device=dev)
+        td[:data.shape[0]] = torch.from_numpy(data).to(dev)
+        tl = torch.zeros(mx_l, dtype=torch.int64, device=dev)
+        tl[:lens.shape[0]] = torch.from_numpy(lens).to(dev)
+        gd = [torch.empty(mx_d, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None
+        gl = [torch.empty(mx_l, dtype=torch.int64, device=dev) for _ in range(world)] if rank == 0 else None
+        dist.gather(td, gd, dst=0)
+        dist.gather(tl, gl, dst=0)
+        if rank != 0:
+            return None, None
+        datas = [gd[k][:allsz[k][0]].cpu().numpy() for k in range(world)]          # slices are contiguous in
+        lens_all = np.concatenate([gl[k][:allsz[k][1]].cpu().numpy() for k in range(world)])   # seed order
+        moff = np.zeros(lens_all.shape[0] + 1, dtype=np.uint64)
+        np.cumsum(lens_all, out=moff[1:])
+        return np.concatenate(datas), moff
 
     def timed(fn, steps):
         barrier()
@@ -252,103 +372,136 @@ def main():
         L.fcx_timer_stop(eng._h, C.byref(ms))
         wall = time.perf_counter() - t0
         barrier()
-        return allmax(ms.value), allmax(wall * 1e3)
+        return allred(ms.value, dist.ReduceOp.MAX), allred(wall * 1e3, dist.ReduceOp.MAX)
 
-    # resident-pool path
-    eng.upload_pool_raw(buf.ptr, off)
-    step_resident = lambda: eng.consensus_blocks_raw(block_off, ids, args.min_cov, args.min_idt)  # noqa: E731
-    for _ in range(args.warmup):
-        step_resident()
+    # ---------------------------------------------------------------- resident-store path
+    build_store()
+    first = run_blocks()
+    for _ in range(max(0, args.warmup - 1)):
+        run_blocks()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    acc = {k: 0.0 for k in ("ms_index", "ms_range", "ms_dp", "ms_traceback", "ms_consensus", "ms_total")}
-    cnt = {}
-
-    def step_resident_stats():
-        step_resident()
-        st = eng.stats()
-        for k in acc:
-            acc[k] += st[k]
-        cnt.update({k: v for k, v in st.items() if not k.startswith("ms_")})
-
-    dev_ms, wall_ms = timed(step_resident, args.steps)
+    dev_ms, wall_ms = timed(run_blocks, args.steps)
     clocks = sampler.stop() if rank == 0 else None
-    total_pairs = allsum(float(n_pairs))
+    total_pairs = allred(float(n_pairs), dist.ReduceOp.SUM)
     value = total_pairs * args.steps / (dev_ms / 1e3)
     # per-kernel CUDA-event times for the roofline: one extra (untimed) step with a single wave in
     # flight, so that the kernel durations are not inflated by overlapping lanes
     eng.set_option("lanes", 1)
-    step_resident_stats()
+    run_blocks()
+    st = eng.stats()
     eng.set_option("lanes", 0)
-    n_kstat = 1
+    kms = {k[3:]: st[k] for k in st if k.startswith("ms_") and k != "ms_total"}
+    cnt = {k: v for k, v in st.items() if not k.startswith("ms_")}
 
-    # e2e path: upload from pinned host memory + consensus + results back, every step
+    # ---------------------------------------------------------------- e2e path
     e2e = None
+    merged = None
     if not args.no_e2e:
         def step_e2e():
-            eng.upload_pool_raw(buf.ptr, off)
-            return eng.consensus_blocks_raw(block_off, ids, args.min_cov, args.min_idt)
-        data, ooff = step_e2e()
+            build_store()
+            d, o = run_blocks()
+            return gather_to_rank0(d, o)
+        merged = step_e2e()
         for _ in range(max(0, args.warmup - 1)):
             step_e2e()
-        e_ms, e_wall = timed(step_e2e, args.steps)
-        h2d = int(off[-1]) + off.nbytes * 2 + block_off.nbytes + ids.nbytes
-        d2h = int(data.nbytes + ooff.nbytes)
-        e2e = {"value": total_pairs * args.steps / (e_wall / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "ms_per_step": e_wall / args.steps, "api": "fcx_pool_upload + fcx_consensus_blocks"}
+        _, e_wall = timed(step_e2e, args.steps)
+        h2d = allred(float(int(poff[-1]) + all_off.nbytes + block_off.nbytes + ids.nbytes), dist.ReduceOp.SUM)
+        d2h = float(merged[0].nbytes + merged[1].nbytes) if rank == 0 else 0.0
+        e2e = {"value": total_pairs * args.steps / (e_wall / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": e_wall / args.steps,
+               "nccl_broadcast_bytes_per_gpu_per_step": bcast_bytes[0],
+               "api": "fcx_pool_reserve/upload_part/commit (+ NCCL broadcast of the packed parts) + "
+                      "fcx_consensus_blocks + ordered gather to rank 0"}
 
-    # roofline of the dominant kernel (algorithmic bytes per SURVEY.md 8(d))
+    # ---------------------------------------------------------------- CPU baseline + PARITY GATE
+    cpu_baseline = None
+    if rank == 0 and not args.no_cpu_baseline:
+        data, off = first
+        raw = data.tobytes()
+        nblk = min(len(blocks), args.cpu_blocks_per_core * cores)
+        sids = list(range(0, len(blocks), max(1, len(blocks) // nblk)))[:nblk]
+        # the sample needs reads of other ranks' parts only if a block reaches past r1: regenerate those
+        need = sorted({int(i) >> 1 for b in sids for i in blocks[b]})
+        extra = {}
+        for r in need:
+            if not (r0 <= r < r1):
+                g = synth.gen_reads(geo, r, r + 1)
+                extra[2 * r], extra[2 * r + 1] = g[0], g[1]
+        reads = lambda i: part[i - 2 * r0] if 2 * r0 <= i < 2 * r1 else extra[i]      # noqa: E731
+        jobs = [([reads(int(i)) for i in blocks[b]], args.min_cov, args.min_idt) for b in sids]
+        pairs = sum(len(j[0]) - 1 for j in jobs)
+        cpu = CpuReference(cores)
+        cpu.run(jobs[:cores])                                       # warm the workers (msa_array init)
+        dt, cpu_s, digests = cpu.run(jobs)
+        one = CpuReference(1)
+        one.run(jobs[:1])
+        dt1, cpu1, _ = one.run(jobs[:args.cpu_blocks_per_core])
+        pairs1 = sum(len(j[0]) - 1 for j in jobs[:args.cpu_blocks_per_core])
+        one.close(); cpu.close()
+        bad = []
+        for b, (md5, ln) in zip(sids, digests):
+            got = raw[int(off[b]):int(off[b + 1])]
+            if len(got) != ln or hashlib.md5(got).hexdigest() != md5:
+                bad.append(b)
+        if merged is not None and world > 1:                        # the merged multi-GPU output must start with rank 0's
+            assert merged[0][:int(off[-1])].tobytes() == raw, "ordered merge differs from rank 0's own output"
+        if bad:
+            print(json.dumps({"error": "PARITY GATE FAILED: GPU consensus differs from the %s CPU code on %d of %d "
+                                       "sampled blocks (first: %d)" % (cpu.kind, len(bad), len(sids), bad[0])}))
+            if world > 1:
+                dist.destroy_process_group()
+            return 3
+        cpu_baseline = {"value": pairs / dt, "unit": UNIT, "cores": cores, "kind": cpu.kind,
+                        "sample": "%d seed blocks (%d pairs) of the same workload, %d per core, %.1f s wall" %
+                                  (len(jobs), pairs, args.cpu_blocks_per_core, dt),
+                        "cpu_model": cpu_model(), "os_cpu_count": os.cpu_count(),
+                        "per_core_pairs_per_cpu_second": pairs / cpu_s,
+                        "one_core": {"value": pairs1 / dt1, "unit": UNIT, "pairs": pairs1},
+                        "parity_gate": "GPU == CPU consensus (md5) on all %d sampled blocks" % len(sids),
+                        "note": "fork pool, imap chunksize 1 (falcon_kit/mains/consensus.py:264-274); job pickling included"}
+
+    # ---------------------------------------------------------------- roofline of the dominant kernel
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    kms = {k[3:]: acc[k] / n_kstat for k in acc if k != "ms_total"}
     dom = max(kms, key=kms.get)
     E, D1, A, SP = cnt.get("trace_cells", 0), cnt.get("dp_steps", 0), cnt.get("aln_cols", 0), cnt.get("span_bases", 0)
-    seed_bases = float(sum(len(S.pool[b[0]]) for b in S.blocks))
+    seed_bases = float(sum(int(noisy[s]) for s in seeds_all[b0:b1]))
     bytes_dp = SP / 4.0 + 4.0 * E + 8.0 * D1 + 8.0 * A
-    bytes_cns = 2 * 8.0 * A + seed_bases
-    alg = {"dp": bytes_dp, "consensus": bytes_cns, "traceback": 4.0 * E / 8 + 8.0 * A, "range": SP / 4.0, "index": seed_bases * 4}
+    alg = {"dp": bytes_dp, "consensus": 2 * 8.0 * A + seed_bases, "traceback": 4.0 * E / 8 + 8.0 * A,
+           "range": SP / 4.0, "index": seed_bases * 4}
     ach = alg.get(dom, 0.0) / (kms[dom] / 1e3) / 1e9 if kms[dom] > 0 else 0.0
     traffic = None
+    kname = {"dp": "k_dp3"}.get(dom, "k_" + dom)
     try:   # dram__bytes_read+write per launch of the dominant kernel, from the committed ncu capture
         prof = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))
-        k = prof.get("k_" + dom)
+        k = prof.get(kname)
         if k:
             traffic = {"bytes_per_launch": k["dram_bytes"], "pairs_in_launch": k.get("pairs"),
                        "bytes_per_pair": k["dram_bytes"] / max(1, k.get("pairs", 1)), "source": "profiles/ncu_summary.json"}
     except Exception:
         pass
-    kname = {"dp": "k_dp2"}.get(dom, "k_" + dom)      # the default DP kernel is the two-pairs-per-warp k_dp2
+    dp_ach = bytes_dp / (kms["dp"] / 1e3) / 1e9 if kms.get("dp", 0) > 0 else 0.0
     roofline = {"kernel": kname, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
                 "frac": ach / peak, "traffic": traffic,
-                "kernel_timing": "CUDA events on the launching stream, one step with a single wave in flight",
+                "kernel_timing": "CUDA events on the launching stream, one step with a single wave in flight (rank 0)",
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
                 "kernel_ms_per_step": kms, "algorithmic_bytes_per_step": alg[dom],
-                "dp_kernel": {"achieved": bytes_dp / (kms["dp"] / 1e3) / 1e9 if kms["dp"] > 0 else 0.0,
-                              "frac": (bytes_dp / (kms["dp"] / 1e3) / 1e9 / peak) if kms["dp"] > 0 else 0.0}}
-
-    cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        pool, kind = cpu_reference_pool(cores)
-        nblk = args.cpu_sample_blocks or min(len(S.blocks), 2 * cores)
-        cpu_reference_time(pool, S, list(range(min(nblk, cores))), args.min_cov, args.min_idt)   # warm the workers
-        pairs, dt = cpu_reference_time(pool, S, list(range(nblk)), args.min_cov, args.min_idt)
-        pool.terminate()
-        cpu_baseline = {"value": pairs / dt, "unit": UNIT, "cores": cores, "kind": kind,
-                        "sample": "%d seed blocks (%d pairs) of the same workload, %.1f s wall" % (nblk, pairs, dt)}
+                "dp_kernel": {"kernel": "k_dp3", "achieved": dp_ach, "frac": dp_ach / peak,
+                              "algorithmic_bytes_per_pair": bytes_dp / max(1, cnt.get("dp_pairs", 1))}}
 
     if rank == 0:
-        aligned_bases = cnt.get("aln_cols", 0)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": config,
-                "pairs_per_step_per_rank": n_pairs, "wall_ms_per_step": wall_ms / args.steps,
+                "scaling": scaling, "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": config,
+                "pairs_per_step": int(total_pairs), "wall_ms_per_step": wall_ms / args.steps,
                 "gbases_per_s_input": value * args.read_len / 1e9,
-                "aligned_columns_per_step_rank0": aligned_bases,
+                "setup_s": {"generate_and_index_rank0": t_gen},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(cnt.get("kernel_launches", 0)) * args.steps,
                 "roofline": roofline, "cpu_baseline": cpu_baseline}
         print(json.dumps(line))

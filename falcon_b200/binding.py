@@ -104,6 +104,10 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.fcx_host_alloc.restype = C.c_void_p
     lib.fcx_host_free.argtypes = [C.c_void_p]
     lib.fcx_pool_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+    lib.fcx_pool_reserve.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64)]
+    lib.fcx_pool_upload_part.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
+    lib.fcx_pool_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_void_p)]
+    lib.fcx_pool_commit.argtypes = [C.c_void_p]
     lib.fcx_consensus_blocks.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint,
                                          C.c_uint, C.c_double, C.POINTER(C.c_void_p),
                                          C.POINTER(C.c_void_p)]
@@ -213,6 +217,32 @@ class Engine:
         cat = b"".join(reads)
         buf = C.create_string_buffer(cat, len(cat) + 1)
         self.upload_pool_raw(C.addressof(buf), offsets)
+
+    # -- pool assembled from parts (multi-process / multi-GPU) -------------
+    def pool_reserve(self, offsets: np.ndarray) -> int:
+        """Fix the pool layout from the lengths of ALL reads; returns the packed size in words."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = offsets.shape[0] - 1
+        w = C.c_uint64()
+        self._check(self._lib.fcx_pool_reserve(self._h, offsets.ctypes.data, n, C.byref(w)), "fcx_pool_reserve")
+        self._reserved = n
+        return int(w.value)
+
+    def pool_upload_part(self, bases_ptr: int, offsets_part: np.ndarray, first_read: int):
+        offsets_part = np.ascontiguousarray(offsets_part, dtype=np.uint64)
+        self._check(self._lib.fcx_pool_upload_part(self._h, bases_ptr, offsets_part.ctypes.data, first_read,
+                                                   offsets_part.shape[0] - 1), "fcx_pool_upload_part")
+
+    def pool_device(self):
+        """-> (device pointer of the packed pool, number of 32-bit words, word offsets per read)."""
+        ptr, nw, wo = C.c_void_p(), C.c_uint64(), C.c_void_p()
+        self._check(self._lib.fcx_pool_device(self._h, C.byref(ptr), C.byref(nw), C.byref(wo)), "fcx_pool_device")
+        woff = np.ctypeslib.as_array((C.c_uint64 * (self._reserved + 1)).from_address(wo.value)).copy()
+        return int(ptr.value), int(nw.value), woff
+
+    def pool_commit(self):
+        self._check(self._lib.fcx_pool_commit(self._h), "fcx_pool_commit")
+        self.n_reads = self._reserved
 
     # -- consensus ----------------------------------------------------------------------
     def consensus_blocks_raw(self, block_off: np.ndarray, read_ids: np.ndarray, min_cov: int,

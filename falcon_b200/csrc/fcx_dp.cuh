@@ -59,15 +59,20 @@ __global__ void __launch_bounds__(DP3_WARPS * 32)
 k_dp3(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs,
       const PairRange* __restrict__ ranges, const PairAlloc* __restrict__ allocs, uint32_t n_pairs,
       const uint32_t* __restrict__ pool, uint32_t* __restrict__ trace_arena, double max_diff,
-      PairAln* __restrict__ out) {
+      uint32_t* __restrict__ next_pair, PairAln* __restrict__ out) {
     __shared__ int s_V[DP3_WARPS][VRING];          // wide mode only
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const uint32_t p = blockIdx.x * DP3_WARPS + wib;
+  // Persistent warps: the grid fills the GPU once and every warp pulls the next pair from a device
+  // counter, so a long pair never holds back a CTA slot and short pairs do not pay a CTA launch.
+  for (;;) {
+    uint32_t p = 0;
+    if (lane == 0) p = atomicAdd(next_pair, 1u);
+    p = __shfl_sync(FULL, p, 0);
     if (p >= n_pairs) return;
     PairAln res; res.aligned = res.dist = res.aln_size = res.q_e = res.t_e = res.k_end = 0;
     res.accepted = res.t_cnt = res.n_tags = res.cells = 0;
     const PairRange rg = ranges[p];
-    if (!rg.pass) { if (lane == 0) out[p] = res; return; }
+    if (!rg.pass) { if (lane == 0) out[p] = res; continue; }
     const PairDesc pd = pairs[p];
     const uint32_t* q = pool + pd.read_woff;
     const uint32_t* t = pool + blocks[pd.block].seed_woff;
@@ -286,6 +291,8 @@ k_dp3(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs,
     }
     res.cells = cells;
     if (lane == 0) out[p] = res;
+    __syncwarp();                       // wide mode: the ring is reused by the next pair
+  }
 }
 
 }  // namespace fcx

@@ -57,7 +57,7 @@ struct Lane {                 // one in-flight wave: stream, events, buffers, st
     cudaStream_t stream_hi = nullptr;   // high priority: the latency-bound consensus kernel
     cudaEvent_t ev[8] = {nullptr};
     DevBuf d_blocks, d_pairs, d_ranges, d_allocs, d_aln, d_ktab, d_kpos, d_trace, d_path, d_xam, d_ent, d_M,
-           d_rlist, d_recs, d_lvl, d_meta, d_cns, d_eqv, d_cnsout;
+           d_rlist, d_recs, d_lvl, d_meta, d_cns, d_eqv, d_cnsout, d_counter;
     HostBuf h_ranges, h_aln, h_cns, h_cnsout, h_eqv;
     std::string err;
     double times[FCX_T_COUNT] = {0};
@@ -65,7 +65,7 @@ struct Lane {                 // one in-flight wave: stream, events, buffers, st
     double prof[8] = {0};
     void release() {
         DevBuf* bufs[] = {&d_blocks, &d_pairs, &d_ranges, &d_allocs, &d_aln, &d_ktab, &d_kpos, &d_trace, &d_path,
-                          &d_xam, &d_ent, &d_M, &d_rlist, &d_recs, &d_lvl, &d_meta, &d_cns, &d_eqv, &d_cnsout};
+                          &d_xam, &d_ent, &d_M, &d_rlist, &d_recs, &d_lvl, &d_meta, &d_cns, &d_eqv, &d_cnsout, &d_counter};
         for (auto* b : bufs) b->release();
         HostBuf* hb[] = {&h_ranges, &h_aln, &h_cns, &h_cnsout, &h_eqv};
         for (auto* b : hb) b->release();
@@ -89,7 +89,8 @@ struct fcx_ctx {
     cudaStream_t stream = nullptr;     // pool uploads, single-pair align, stopwatch
     std::string err;
     // pool
-    uint32_t n_reads = 0;
+    uint32_t n_reads = 0;              // committed pool size
+    uint32_t n_reserved = 0;           // reads in the reserved layout (fcx_pool_reserve)
     std::vector<uint64_t> h_woff;      // n_reads + 1
     std::vector<int32_t> h_len;
     DevBuf d_pool, d_ascii, d_aoff, d_woff, d_len, d_dirty;
@@ -171,7 +172,17 @@ extern "C" int fcx_create(int device, fcx_ctx** out) {
         g_create_err = "cudaSetDevice/cudaStreamCreate failed";
         delete ctx; return 1;
     }
-    for (auto& ev : ctx->tev) cudaEventCreate(&ev);
+    // every CUDA call below is checked: a failure here would otherwise surface later as an
+    // unrelated launch or event error
+#define CKC(call)                                                                          \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess) {                                                           \
+            g_create_err = std::string(#call " failed: ") + cudaGetErrorString(e_);        \
+            fcx_destroy(ctx); return 1;                                                    \
+        }                                                                                  \
+    } while (0)
+    for (auto& ev : ctx->tev) CKC(cudaEventCreate(&ev));
     if (const char* s = getenv("FCX_ARENA_GB")) ctx->arena_budget = (size_t)(atof(s) * (double)((size_t)1 << 30));
     if (const char* s = getenv("FCX_WAVE_BLOCKS")) { ctx->max_wave_blocks = (uint32_t)atoi(s); ctx->min_wave_blocks = std::min(ctx->min_wave_blocks, ctx->max_wave_blocks); }
     if (const char* s = getenv("FCX_WAVE_PAIRS")) ctx->max_wave_pairs = (uint32_t)atoi(s);
@@ -179,27 +190,26 @@ extern "C" int fcx_create(int device, fcx_ctx** out) {
     if (const char* s = getenv("FCX_PROFILE")) ctx->profile = atoi(s) != 0;
     if (const char* s = getenv("FCX_DP_VARIANT")) ctx->dp_variant = atoi(s);
 #ifndef FCX_EMU
-    cudaFuncSetAttribute(k_dp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    CKC(cudaFuncSetAttribute(k_dp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
 #endif
-    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    CKC(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
     if (!getenv("FCX_WAVE_BLOCKS")) ctx->max_wave_blocks = (uint32_t)(ctx->sm_count * CNS_CTAS_PER_SM * CNS_WARPS);
     {   // never plan beyond what the device can actually give
         size_t free_b = 0, total_b = 0;
-        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && !getenv("FCX_ARENA_GB"))
-            ctx->arena_budget = std::min(ctx->arena_budget, (size_t)((double)free_b * 0.70));
+        CKC(cudaMemGetInfo(&free_b, &total_b));
+        if (!getenv("FCX_ARENA_GB")) ctx->arena_budget = std::min(ctx->arena_budget, (size_t)((double)free_b * 0.70));
     }
-    cudaFuncSetAttribute(k_range, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         RANGE_WARPS * RANGE_BINS * (int)sizeof(int));
+    CKC(cudaFuncSetAttribute(k_range, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             RANGE_WARPS * RANGE_BINS * (int)sizeof(int)));
     ctx->lanes.resize(ctx->n_lanes);
     int prio_lo = 0, prio_hi = 0;
-    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    CKC(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     for (auto& L : ctx->lanes) {
-        if (cudaStreamCreateWithPriority(&L.stream, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
-            cudaStreamCreateWithPriority(&L.stream_hi, cudaStreamNonBlocking, prio_hi) != cudaSuccess) {
-            g_create_err = "cudaStreamCreate (lane) failed"; fcx_destroy(ctx); return 1;
-        }
-        for (auto& ev : L.ev) cudaEventCreate(&ev);
+        CKC(cudaStreamCreateWithPriority(&L.stream, cudaStreamNonBlocking, prio_lo));
+        CKC(cudaStreamCreateWithPriority(&L.stream_hi, cudaStreamNonBlocking, prio_hi));
+        for (auto& ev : L.ev) CKC(cudaEventCreate(&ev));
     }
+#undef CKC
     *out = ctx;
     return 0;
 }
@@ -240,47 +250,91 @@ extern "C" int fcx_set_option(fcx_ctx* ctx, const char* name, double value) {
 }
 
 // ---------------------------------------------------------------------------------- pool
-extern "C" int fcx_pool_upload(fcx_ctx* ctx, const char* bases, const uint64_t* offsets, uint32_t n_reads) {
+// The pool is built in three steps so that several processes / devices can each contribute a part
+// (one NCCL broadcast or peer copy per part): reserve (layout from the read lengths),
+// upload_part (ASCII of a contiguous range of reads -> packed in place), commit.
+extern "C" int fcx_pool_reserve(fcx_ctx* ctx, const uint64_t* offsets, uint32_t n_reads, uint64_t* total_words) {
     CK(cudaSetDevice(ctx->device));
-    ctx->n_reads = 0;
+    ctx->n_reads = 0; ctx->n_reserved = 0;
     ctx->h_woff.assign((size_t)n_reads + 1, 0);
     ctx->h_len.assign(n_reads, 0);
     uint64_t w = 0;
     for (uint32_t r = 0; r < n_reads; r++) {
         uint64_t len = offsets[r + 1] - offsets[r];
-        if (len >= 100000) { ctx->err = "read longer than 99999 bases (the reference truncates at consensus.py:178-179 and asserts at falcon.c:343)"; return 1; }
+        // the reference truncates reads at 100000 bases (consensus.py:178-179) and asserts
+        // t_len < 100000 for the seed only (falcon.c:343): seeds are checked per block
+        if (len > 100000) { ctx->err = "read longer than 100000 bases (the reference truncates at consensus.py:178-179)"; return 1; }
         ctx->h_len[r] = (int32_t)len;
         ctx->h_woff[r] = w;
         uint64_t words = (len + 15) / 16 + 1;            // +1 zero pad word: fetch16 reads one word ahead
         w += (words + 3) & ~(uint64_t)3;                 // 16-byte aligned starts
     }
     ctx->h_woff[n_reads] = w;
-    const uint64_t total_bytes = offsets[n_reads] - offsets[0];
     CK(ctx->d_pool.reserve((w + 4) * 4));
-    CK(ctx->d_ascii.reserve(total_bytes + 16));
-    CK(ctx->d_aoff.reserve(((size_t)n_reads + 1) * 8));
-    CK(ctx->d_woff.reserve(((size_t)n_reads + 1) * 8));
-    CK(ctx->d_len.reserve((size_t)n_reads * 4 + 4));
     CK(ctx->d_dirty.reserve(4));
-    std::vector<uint64_t> rel((size_t)n_reads + 1);
-    for (uint32_t r = 0; r <= n_reads; r++) rel[r] = offsets[r] - offsets[0];
+    CK(cudaMemsetAsync((char*)ctx->d_pool.p + w * 4, 0, 16, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->n_reserved = n_reads;
+    if (total_words) *total_words = w;
+    return 0;
+}
+
+extern "C" int fcx_pool_upload_part(fcx_ctx* ctx, const char* bases, const uint64_t* offsets, uint32_t first_read,
+                                    uint32_t n_part) {
+    CK(cudaSetDevice(ctx->device));
+    if ((uint64_t)first_read + n_part > ctx->n_reserved) { ctx->err = "fcx_pool_upload_part: range outside the reserved pool"; return 1; }
+    if (n_part == 0) return 0;
+    for (uint32_t r = 0; r < n_part; r++)
+        if ((int64_t)(offsets[r + 1] - offsets[r]) != (int64_t)ctx->h_len[first_read + r]) {
+            ctx->err = "fcx_pool_upload_part: read length differs from the reserved layout"; return 1;
+        }
+    const uint64_t total_bytes = offsets[n_part] - offsets[0];
+    const uint64_t w0 = ctx->h_woff[first_read], w1 = ctx->h_woff[first_read + n_part];
+    CK(ctx->d_ascii.reserve(total_bytes + 16));
+    CK(ctx->d_aoff.reserve(((size_t)n_part + 1) * 8));
+    CK(ctx->d_woff.reserve(((size_t)n_part + 1) * 8));
+    CK(ctx->d_len.reserve((size_t)n_part * 4 + 4));
+    std::vector<uint64_t> rel((size_t)n_part + 1), wrel((size_t)n_part + 1);
+    for (uint32_t r = 0; r <= n_part; r++) { rel[r] = offsets[r] - offsets[0]; wrel[r] = ctx->h_woff[first_read + r] - w0; }
     CK(cudaMemcpyAsync(ctx->d_ascii.p, bases + offsets[0], total_bytes, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_aoff.p, rel.data(), rel.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->d_woff.p, ctx->h_woff.data(), ctx->h_woff.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->d_len.p, ctx->h_len.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_woff.p, wrel.data(), wrel.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_len.p, ctx->h_len.data() + first_read, (size_t)n_part * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_dirty.p, 0, 4, ctx->stream));
-    CK(cudaMemsetAsync((char*)ctx->d_pool.p + w * 4, 0, 16, ctx->stream));
-    if (w > 0) {
-        uint64_t nb = (w + 255) / 256;
+    if (w1 > w0) {
+        const uint64_t nb = (w1 - w0 + 255) / 256;
         FCX_LAUNCH(k_pack, (unsigned)nb, 256, 0, ctx->stream, ctx->d_ascii.as<uint8_t>(), ctx->d_aoff.as<uint64_t>(),
-                                                      ctx->d_woff.as<uint64_t>(), ctx->d_len.as<int32_t>(), n_reads, w,
-                                                      ctx->d_pool.as<uint32_t>(), ctx->d_dirty.as<int>());
+                   ctx->d_woff.as<uint64_t>(), ctx->d_len.as<int32_t>(), n_part, w1 - w0,
+                   ctx->d_pool.as<uint32_t>() + w0, ctx->d_dirty.as<int>());
         CK(cudaGetLastError());
     }
     int dirty = 0;
     CK(cudaMemcpyAsync(&dirty, ctx->d_dirty.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     if (dirty) { ctx->err = "read pool contains bytes outside upper-case ACGT (reference behaviour undefined: falcon.c:370-379)"; return 2; }
+    return 0;
+}
+
+// Device view of the packed pool (for a collective or a peer copy issued by the caller): base
+// pointer, number of 32-bit words, and the host array of n_reads + 1 word offsets.
+extern "C" int fcx_pool_device(fcx_ctx* ctx, void** dev_words, uint64_t* n_words, const uint64_t** word_off) {
+    if (!ctx->n_reserved) { ctx->err = "fcx_pool_device: no pool reserved"; return 1; }
+    if (dev_words) *dev_words = ctx->d_pool.p;
+    if (n_words) *n_words = ctx->h_woff[ctx->n_reserved];
+    if (word_off) *word_off = ctx->h_woff.data();
+    return 0;
+}
+
+extern "C" int fcx_pool_commit(fcx_ctx* ctx) {
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    ctx->n_reads = ctx->n_reserved;
+    return 0;
+}
+
+extern "C" int fcx_pool_upload(fcx_ctx* ctx, const char* bases, const uint64_t* offsets, uint32_t n_reads) {
+    if (int rc = fcx_pool_reserve(ctx, offsets, n_reads, nullptr)) return rc;
+    if (int rc = fcx_pool_upload_part(ctx, bases, offsets, 0, n_reads)) return rc;
     ctx->n_reads = n_reads;
     return 0;
 }
@@ -410,10 +464,13 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
     if (np) {
         if (ctx->dp_variant == 3) {
             // default: one warp per pair, diagonals pinned to lanes, V in registers (fcx_dp.cuh)
-            FCX_LAUNCH(k_dp3, (np + DP3_WARPS - 1) / DP3_WARPS, DP3_WARPS * 32, 0, st,
+            CKR(L.d_counter.reserve(64));
+            CKL(cudaMemsetAsync(L.d_counter.p, 0, 64, st));
+            const unsigned dp_grid = std::min<unsigned>((np + DP3_WARPS - 1) / DP3_WARPS, (unsigned)ctx->sm_count * 32u);
+            FCX_LAUNCH(k_dp3, dp_grid, DP3_WARPS * 32, 0, st,
                        L.d_blocks.as<BlockDesc>(), L.d_pairs.as<PairDesc>(), L.d_ranges.as<PairRange>(),
                        L.d_allocs.as<PairAlloc>(), np, pool, L.d_trace.as<uint32_t>(), 1.0 - min_idt,
-                       L.d_aln.as<PairAln>());
+                       L.d_counter.as<uint32_t>(), L.d_aln.as<PairAln>());
         } else {
             // round-1 kernels kept for A/B measurement: shared-memory V ring, lanes re-mapped to the
             // band every step; dp_variant 2 stages the spans through TMA when they fit
@@ -556,6 +613,7 @@ extern "C" int fcx_consensus_blocks(fcx_ctx* ctx, uint32_t n_blocks, const uint3
         if (block_off[b + 1] - block_off[b] > 65000) { ctx->err = "more than 65000 reads in one block"; return 1; }
         for (uint32_t i = block_off[b]; i < block_off[b + 1]; i++)
             if (read_ids[i] >= ctx->n_reads) { ctx->err = "read id outside the uploaded pool"; return 1; }
+        if (ctx->h_len[read_ids[block_off[b]]] >= 100000) { ctx->err = "seed of 100000 bases or more (the reference asserts t_len < 100000, falcon.c:343)"; return 1; }
     }
     // ---- plan waves from upper bounds (exact sizes are computed per wave after k_range).
     // Aim for >= 2 waves per lane so that stages of different waves overlap, but keep waves large

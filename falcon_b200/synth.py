@@ -89,17 +89,28 @@ class SynthSet:
         return b"".join(out)
 
 
-def make_set(genome_size: int, read_len: int, coverage: float, seed: int = 20260924,
-             n_blocks: Optional[int] = None, min_ovl: int = 1000, max_n_read: int = 200,
-             len_sigma: float = 0.0, p_ins: float = 0.09, p_del: float = 0.045,
-             p_sub: float = 0.015, block_stride: int = 1) -> SynthSet:
-    """Build a synthetic set.  Each read contributes two pool entries (forward-strand noisy copy
-    and its reverse complement); a block uses the orientation of its seed for every member.
+@dataclass
+class Geometry:
+    """Where every read of a synthetic set lies on the genome.  A pure function of the parameters
+    and the seed, so every rank of a multi-GPU job can compute it independently."""
+    genome: np.ndarray
+    starts: np.ndarray
+    lens: np.ndarray
+    ends: np.ndarray
+    strands: np.ndarray
+    seed: int
+    p_ins: float
+    p_del: float
+    p_sub: float
 
-    Block layout mirrors what get_seq_data + get_longest_reads produce
-    (consensus.py:26-45,161-209): ``[seed, seed, reads sorted by -len (stable)]`` capped at
-    ``max_n_read`` entries.
-    """
+    @property
+    def n_reads(self) -> int:
+        return int(self.starts.shape[0])
+
+
+def make_geometry(genome_size: int, read_len: int, coverage: float, seed: int = 20260924,
+                  len_sigma: float = 0.0, p_ins: float = 0.09, p_del: float = 0.045,
+                  p_sub: float = 0.015) -> Geometry:
     rng = np.random.default_rng(seed)
     genome = random_codes(genome_size, rng)
     n_reads = max(2, int(round(genome_size * coverage / read_len)))
@@ -112,27 +123,36 @@ def make_set(genome_size: int, read_len: int, coverage: float, seed: int = 20260
     starts = (rng.random(n_reads) * (genome_size - lens + 1)).astype(np.int64)
     order = np.argsort(starts, kind="stable")
     starts, lens = starts[order], lens[order]
-    ends = starts + lens
     strands = rng.integers(0, 2, n_reads)
+    return Geometry(genome, starts, lens, starts + lens, strands, seed, p_ins, p_del, p_sub)
 
-    pool: List[bytes] = []
-    noisy_len = np.zeros(n_reads, dtype=np.int64)
-    for r in range(n_reads):
-        fwd = add_errors(genome[starts[r]:ends[r]], rng, p_ins, p_del, p_sub)
+
+def gen_reads(geo: Geometry, r0: int, r1: int) -> List[bytes]:
+    """Noisy copies of reads r0..r1-1: two pool entries per read (forward, reverse complement).
+    Every read has its own RNG stream keyed by (seed, read index): any rank can generate any slice
+    and gets exactly the bytes every other rank would."""
+    out: List[bytes] = []
+    for r in range(r0, r1):
+        rng = np.random.default_rng([geo.seed, r])
+        fwd = add_errors(geo.genome[geo.starts[r]:geo.ends[r]], rng, geo.p_ins, geo.p_del, geo.p_sub)
         if fwd.shape[0] > 99998:
             fwd = fwd[:99998]
-        noisy_len[r] = fwd.shape[0]
-        pool.append(codes_to_bytes(fwd))
-        pool.append(codes_to_bytes(revcomp_codes(fwd)))
+        out.append(codes_to_bytes(fwd))
+        out.append(codes_to_bytes(revcomp_codes(fwd)))
+    return out
 
+
+def build_blocks(geo: Geometry, noisy_len: np.ndarray, seeds: Sequence[int], min_ovl: int = 1000,
+                 max_n_read: int = 200) -> Tuple[List[np.ndarray], List[str], List[np.ndarray]]:
+    """Seed blocks from ground truth.  Block layout mirrors what get_seq_data + get_longest_reads
+    produce (consensus.py:26-45,161-209): ``[seed, seed, reads sorted by -len (stable)]`` capped at
+    ``max_n_read`` entries.  ``noisy_len[r]`` = length of read r's noisy copy."""
+    starts, ends = geo.starts, geo.ends
     blocks: List[np.ndarray] = []
     seed_ids: List[str] = []
     streams: List[np.ndarray] = []
-    max_len = int(lens.max())
-    seeds = range(0, n_reads, block_stride)
+    max_len = int(geo.lens.max())
     for s in seeds:
-        if n_blocks is not None and len(blocks) >= n_blocks:
-            break
         lo = int(np.searchsorted(starts, starts[s] - max_len, side="left"))
         hi = int(np.searchsorted(starts, ends[s], side="left"))
         cand = np.arange(lo, hi)
@@ -140,19 +160,35 @@ def make_set(genome_size: int, read_len: int, coverage: float, seed: int = 20260
         members = cand[(ovl >= min_ovl) & (cand != s)]
         # stable sort by -len, as get_longest_reads does on the noisy sequences
         members = members[np.argsort(-noisy_len[members], kind="stable")]
-        o = int(strands[s])  # 0: forward copies, 1: reverse-complement copies
+        o = int(geo.strands[s])  # 0: forward copies, 1: reverse-complement copies
         idx = [2 * s + o, 2 * s + o] + [2 * int(m) + o for m in members]
         stream = np.asarray([idx[0]] + idx[2:], dtype=np.int32)
         # the duplicated seed copy takes part in the stable sort too (it is seqs[1])
         rest = idx[1:]
-        rest_len = np.array([len(pool[i]) for i in rest])
+        rest_len = np.array([noisy_len[i >> 1] for i in rest])
         rest = [rest[i] for i in np.argsort(-rest_len, kind="stable")]
-        idx = [idx[0]] + rest
-        idx = idx[:max_n_read]
+        idx = ([idx[0]] + rest)[:max_n_read]
         blocks.append(np.asarray(idx, dtype=np.int32))
         seed_ids.append("%08d" % s)
         streams.append(stream)
+    return blocks, seed_ids, streams
+
+
+def make_set(genome_size: int, read_len: int, coverage: float, seed: int = 20260924,
+             n_blocks: Optional[int] = None, min_ovl: int = 1000, max_n_read: int = 200,
+             len_sigma: float = 0.0, p_ins: float = 0.09, p_del: float = 0.045,
+             p_sub: float = 0.015, block_stride: int = 1) -> SynthSet:
+    """Build a synthetic set in one process.  Each read contributes two pool entries
+    (forward-strand noisy copy and its reverse complement); a block uses the orientation of its
+    seed for every member."""
+    geo = make_geometry(genome_size, read_len, coverage, seed, len_sigma, p_ins, p_del, p_sub)
+    pool = gen_reads(geo, 0, geo.n_reads)
+    noisy_len = np.fromiter((len(pool[2 * r]) for r in range(geo.n_reads)), dtype=np.int64, count=geo.n_reads)
+    seeds = list(range(0, geo.n_reads, block_stride))
+    if n_blocks is not None:
+        seeds = seeds[:n_blocks]
+    blocks, seed_ids, streams = build_blocks(geo, noisy_len, seeds, min_ovl, max_n_read)
     return SynthSet(pool=pool, blocks=blocks, seed_ids=seed_ids, streams=streams, read_len=read_len,
                     genome_size=genome_size,
                     meta=dict(seed=seed, coverage=coverage, p_ins=p_ins, p_del=p_del, p_sub=p_sub,
-                              min_ovl=min_ovl, max_n_read=max_n_read, n_reads=n_reads))
+                              min_ovl=min_ovl, max_n_read=max_n_read, n_reads=geo.n_reads))

@@ -124,6 +124,22 @@ void fcx_host_free(void *);
  * indexes base[-1]). */
 int fcx_pool_upload(fcx_ctx *, const char *bases, const uint64_t *offsets, uint32_t n_reads);
 
+/* The same in three steps, for pools assembled from parts (several processes / devices each
+ * holding some of the reads; SURVEY.md 8(e): "one broadcast of the read index"):
+ *   reserve      fixes the layout from the read lengths (offsets as above; no data is read) and
+ *                returns the size of the packed pool in 32-bit words;
+ *   upload_part  uploads and packs reads [first_read, first_read + n_part) -- `bases`/`offsets`
+ *                describe just that part;
+ *   device       exposes the packed pool (device pointer, word count, host array of n_reads + 1
+ *                word offsets) so that the caller can fill the parts it did not upload with a
+ *                collective (NCCL broadcast) or a peer copy straight into place;
+ *   commit       makes the pool usable by fcx_consensus_blocks. */
+int fcx_pool_reserve(fcx_ctx *, const uint64_t *offsets, uint32_t n_reads, uint64_t *total_words);
+int fcx_pool_upload_part(fcx_ctx *, const char *bases, const uint64_t *offsets, uint32_t first_read,
+                         uint32_t n_part);
+int fcx_pool_device(fcx_ctx *, void **dev_words, uint64_t *n_words, const uint64_t **word_off);
+int fcx_pool_commit(fcx_ctx *);
+
 /* Consensus for n_blocks seed blocks.  Block b consists of pool reads
  * read_ids[block_off[b] .. block_off[b+1]); the first is the seed (target), the rest are aligned
  * to it in order (exactly the char** order of the reference's generate_consensus).

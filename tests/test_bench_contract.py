@@ -8,7 +8,7 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SMALL = ["--genome", "40000", "--read-len", "3000", "--cov", "15", "--blocks", "4", "--cpu-sample-blocks", "3"]
+SMALL = ["--genome", "40000", "--read-len", "3000", "--cov", "15", "--blocks", "4", "--cpu-blocks-per-core", "1"]
 
 
 def test_reference_arm_json_line():
