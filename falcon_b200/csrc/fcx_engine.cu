@@ -56,16 +56,19 @@ struct Lane {                 // one in-flight wave: stream, events, buffers, st
     cudaStream_t stream = nullptr;
     cudaStream_t stream_hi = nullptr;   // high priority: the latency-bound consensus kernel
     cudaEvent_t ev[8] = {nullptr};
-    DevBuf d_blocks, d_pairs, d_ranges, d_allocs, d_aln, d_ktab, d_kpos, d_trace, d_path, d_xam, d_ent, d_M,
-           d_rlist, d_recs, d_lvl, d_meta, d_cns, d_eqv, d_cnsout, d_counter;
+    DevBuf d_blocks, d_pairs, d_ranges, d_allocs, d_aln, d_ktab, d_kpos, d_trace, d_path, d_xam, d_ent, d_slots,
+           d_ovf, d_vmeta, d_rlist, d_recs, d_lvl, d_cns, d_eqv, d_cnsout, d_counter;
     HostBuf h_ranges, h_aln, h_cns, h_cnsout, h_eqv;
     std::string err;
     double times[FCX_T_COUNT] = {0};
     uint64_t counters[FCX_C_COUNT] = {0};
     double prof[8] = {0};
+    uint32_t ovf_scale = 1;            // size factor of the vote overflow arena (doubled on retry)
+    uint32_t rec_scale = 1;            // size factor of the consensus record arena (doubled on retry)
     void release() {
         DevBuf* bufs[] = {&d_blocks, &d_pairs, &d_ranges, &d_allocs, &d_aln, &d_ktab, &d_kpos, &d_trace, &d_path,
-                          &d_xam, &d_ent, &d_M, &d_rlist, &d_recs, &d_lvl, &d_meta, &d_cns, &d_eqv, &d_cnsout, &d_counter};
+                          &d_xam, &d_ent, &d_slots, &d_ovf, &d_vmeta, &d_rlist, &d_recs, &d_lvl, &d_cns, &d_eqv, &d_cnsout,
+                          &d_counter};
         for (auto* b : bufs) b->release();
         HostBuf* hb[] = {&h_ranges, &h_aln, &h_cns, &h_cnsout, &h_eqv};
         for (auto* b : hb) b->release();
@@ -118,6 +121,7 @@ struct fcx_ctx {
     int active_lanes = 0;              // 0 = all
     int dp_variant = 3;                // 3: k_dp3 (default); 1: k_dp (round-1 kernel); 2: k_dp with TMA-staged spans
     uint32_t debug_split_above = 0;    // test hook: pretend waves with more blocks than this do not fit
+    bool debug_tiny_capacity = false;  // test hook: start every wave with arenas that are too small
 };
 
 static thread_local std::string g_create_err;
@@ -193,7 +197,7 @@ extern "C" int fcx_create(int device, fcx_ctx** out) {
     CKC(cudaFuncSetAttribute(k_dp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
 #endif
     CKC(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
-    if (!getenv("FCX_WAVE_BLOCKS")) ctx->max_wave_blocks = (uint32_t)(ctx->sm_count * CNS_CTAS_PER_SM * CNS_WARPS);
+    if (!getenv("FCX_WAVE_BLOCKS")) ctx->max_wave_blocks = (uint32_t)(ctx->sm_count * 20);
     {   // never plan beyond what the device can actually give
         size_t free_b = 0, total_b = 0;
         CKC(cudaMemGetInfo(&free_b, &total_b));
@@ -244,6 +248,7 @@ extern "C" int fcx_set_option(fcx_ctx* ctx, const char* name, double value) {
     else if (n == "min_wave_blocks") ctx->min_wave_blocks = (uint32_t)value;
     else if (n == "dp_variant") { if (value != 1 && value != 2 && value != 3) { ctx->err = "dp_variant must be 1, 2 or 3"; return 1; } ctx->dp_variant = (int)value; }
     else if (n == "debug_split_above") ctx->debug_split_above = (uint32_t)value;
+    else if (n == "debug_tiny_capacity") ctx->debug_tiny_capacity = value != 0;
     else if (n == "lanes") ctx->active_lanes = value <= 0 ? 0 : std::min((int)value, (int)ctx->lanes.size());
     else { ctx->err = "unknown option: " + n; return 1; }
     return 0;
@@ -349,7 +354,7 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
     const uint32_t nb = b1 - b0;
     if (ctx->debug_split_above && nb > ctx->debug_split_above) { L.err = "out of device memory (simulated)"; return 100; }
     std::vector<BlockDesc> hb(nb);
-    uint64_t npairs64 = 0, kpos_total = 0, rec_total = 0, cns_total = 0, m_total = 0, tiles = 0;
+    uint64_t npairs64 = 0, kpos_total = 0, rec_total = 0, cns_total = 0, slot_total = 0, tiles = 0;
     uint32_t max_np = 1; int max_slen = 1, max_rlen = 1;
     for (uint32_t b = 0; b < nb; b++) {
         uint32_t lo = block_off[b0 + b], hi = block_off[b0 + b + 1];
@@ -363,12 +368,13 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
         // consensus column records: live (position, delta, base) columns.  Measured ~4 per position
         // at 50x; the number grows with coverage (every column needs a vote), hence the n_pairs term.
         // k_consensus reports an overflow as an error, it never drops a column.
-        d.rec_cap = (uint32_t)std::max<int64_t>(64, (int64_t)d.slen * (8 + (int64_t)d.n_pairs / 16) + 64);
+        d.rec_cap = (uint32_t)std::min<int64_t>(0x7fffffff, (int64_t)L.rec_scale * std::max<int64_t>(64, (int64_t)d.slen * (8 + (int64_t)d.n_pairs / 16) + 64));
+        if (ctx->debug_tiny_capacity && L.rec_scale == 1) d.rec_cap = 64;
         d.rec_off = rec_total; rec_total += d.rec_cap;
         d.cns_off = cns_total; cns_total += (uint64_t)d.slen * 2 + 8;
-        d.rb_pad = (d.n_pairs + 31u) & ~31u;
-        d.m_off = m_total; m_total += (uint64_t)d.rb_pad * (uint64_t)std::max(d.slen, 1);
-        d.tile_begin = (uint32_t)tiles; tiles += (uint64_t)((d.slen + 31) / 32) * (d.rb_pad / 32);
+        d.pad_ = 0;
+        d.slot_off = slot_total; slot_total += (uint64_t)std::max(d.slen, 1);
+        d.tile_begin = (uint32_t)tiles; tiles += (uint64_t)((d.slen + VOTE_TP - 1) / VOTE_TP);
         npairs64 += d.n_pairs;
         max_np = std::max(max_np, d.n_pairs);
         max_slen = std::max(max_slen, d.slen);
@@ -397,9 +403,14 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
     CKR(L.d_cns.reserve(cns_total));
     CKR(L.d_eqv.reserve(cns_total * 4));
     CKR(L.d_cnsout.reserve(nb * sizeof(CnsOut)));
-    const uint32_t cns_grid = (nb + CNS_WARPS - 1) / CNS_WARPS;
-    CKR(L.d_lvl.reserve((size_t)cns_grid * CNS_WARPS * 4 * LVL * 4));
-    CKR(L.d_meta.reserve((size_t)cns_grid * CNS_WARPS * max_np * sizeof(ReadMeta)));
+    CKR(L.d_lvl.reserve((size_t)nb * 4 * CDP_LEVELS * 5 * 4));
+    CKR(L.d_vmeta.reserve(np1 * sizeof(VoteMeta)));
+    CKR(L.d_slots.reserve(slot_total * VSLOT * sizeof(uint2) + 64));
+    // links beyond the 15 of a position's own slot: rare (deep coverage); sized generously, and an
+    // overflow is reported (err 2) so that the caller can retry with a larger arena
+    const uint32_t ovf_cap = (uint32_t)std::min<uint64_t>((uint64_t)L.ovf_scale * std::max<uint64_t>(1u << 20, slot_total * 2), 0x7fffffffu);
+    CKR(L.d_ovf.reserve((size_t)ovf_cap * sizeof(uint2)));
+    const uint32_t ovf_cap_used = (ctx->debug_tiny_capacity && L.ovf_scale == 1) ? 8u : ovf_cap;
     CKL(L.h_ranges.reserve(np1 * sizeof(PairRange)));
     CKL(L.h_aln.reserve(np1 * sizeof(PairAln)));
     CKL(L.h_cns.reserve(cns_total));
@@ -457,7 +468,6 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
     CKR(L.d_xam.reserve(xam_n * 4 + 128));
     CKR(L.d_ent.reserve(xam_n * 4 + 128));
     CKR(L.d_path.reserve(path_w * 4 + 64));
-    CKR(L.d_M.reserve(m_total * 4 + 64));
     if (np) CKL(cudaMemcpyAsync(L.d_allocs.p, ha.data(), (size_t)np * sizeof(PairAlloc), cudaMemcpyHostToDevice, st));
     // ---- DP
     CKL(cudaEventRecord(L.ev[3], st));
@@ -496,41 +506,42 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
         L.counters[FCX_C_KERNEL_LAUNCHES] += 1;
     }
     CKL(cudaEventRecord(L.ev[4], st));
-    // ---- traceback + transpose
+    // ---- traceback
     if (np) {
         const uint64_t n16 = (xam_n + 3) / 4 + 1;
-        FCX_LAUNCH(k_fill32, (unsigned)std::min<uint64_t>((n16 + 255) / 256, (uint64_t)ctx->sm_count * 16), 256, 0, st, 
+        FCX_LAUNCH(k_fill32, (unsigned)std::min<uint64_t>((n16 + 255) / 256, (uint64_t)ctx->sm_count * 16), 256, 0, st,
             L.d_ent.as<uint4>(), n16, ENT_PLAIN);
         CKL(cudaGetLastError());
         L.counters[FCX_C_KERNEL_LAUNCHES] += 1;
-        FCX_LAUNCH(k_traceback, (np + 127) / 128, 128, 0, st, 
+        CKL(cudaMemsetAsync(L.d_vmeta.p, 0, (size_t)np * sizeof(VoteMeta), st));
+        FCX_LAUNCH(k_traceback, (np + 127) / 128, 128, 0, st,
             L.d_blocks.as<BlockDesc>(), L.d_pairs.as<PairDesc>(), L.d_ranges.as<PairRange>(),
             L.d_allocs.as<PairAlloc>(), np, pool, L.d_trace.as<uint32_t>(), L.d_path.as<uint32_t>(),
-            L.d_xam.as<uint32_t>(), L.d_ent.as<uint32_t>(), L.d_aln.as<PairAln>());
-        CKL(cudaGetLastError());
-        L.counters[FCX_C_KERNEL_LAUNCHES] += 1;
-    }
-    if (tiles) {
-        FCX_LAUNCH(k_transpose, (unsigned)((tiles + TR_WARPS - 1) / TR_WARPS), TR_WARPS * 32, 0, st, 
-            L.d_blocks.as<BlockDesc>(), nb, (uint32_t)tiles, L.d_ranges.as<PairRange>(),
-            L.d_allocs.as<PairAlloc>(), L.d_aln.as<PairAln>(), L.d_ent.as<uint32_t>(), L.d_M.as<uint32_t>());
+            L.d_xam.as<uint32_t>(), L.d_ent.as<uint32_t>(), L.d_vmeta.as<VoteMeta>(), L.d_aln.as<PairAln>());
         CKL(cudaGetLastError());
         L.counters[FCX_C_KERNEL_LAUNCHES] += 1;
     }
     CKL(cudaEventRecord(L.ev[5], st));
-    // ---- consensus: on the lane's high-priority stream so that its few, long-running CTAs are
-    // placed ahead of the next wave's bulk kernels and overlap them
-    cudaStream_t sh = L.stream_hi;
-    CKL(cudaStreamWaitEvent(sh, L.ev[5], 0));
-    {
-        auto kfn = ctx->profile ? k_consensus<true> : k_consensus<false>;
-        FCX_LAUNCH(kfn, cns_grid, CNS_WARPS * 32, 0, sh, 
-            L.d_blocks.as<BlockDesc>(), nb, L.d_pairs.as<PairDesc>(), L.d_ranges.as<PairRange>(),
-            L.d_allocs.as<PairAlloc>(), L.d_aln.as<PairAln>(), pool, L.d_xam.as<uint32_t>(),
-            L.d_ent.as<uint32_t>(), L.d_M.as<uint32_t>(), L.d_recs.as<CnsRec>(), L.d_lvl.as<int32_t>(),
-            L.d_meta.as<ReadMeta>(), (uint64_t)max_np, L.d_cns.as<char>(), L.d_eqv.as<int32_t>(), min_cov,
-            L.d_cnsout.as<CnsOut>());
+    // ---- consensus: the column vote (parallel over positions), then the serial longest-path DP and
+    // backtrack (one thread per seed block) on the lane's high-priority stream, so that its few
+    // long-running warps are placed ahead of the next wave's bulk kernels and overlap them
+    CKR(L.d_counter.reserve(64));
+    CKL(cudaMemsetAsync((char*)L.d_counter.p + 16, 0, 16, st));      // [4] overflow cursor, [5] vote error flag
+    if (tiles) {
+        FCX_LAUNCH(k_vote, (unsigned)tiles, VOTE_TP, 0, st,
+            L.d_blocks.as<BlockDesc>(), nb, (uint32_t)tiles, L.d_vmeta.as<VoteMeta>(), pool, L.d_xam.as<uint32_t>(),
+            L.d_ent.as<uint32_t>(), L.d_slots.as<uint2>(), L.d_ovf.as<uint2>(), ovf_cap_used,
+            L.d_counter.as<uint32_t>() + 4, L.d_counter.as<int>() + 5);
+        CKL(cudaGetLastError());
+        L.counters[FCX_C_KERNEL_LAUNCHES] += 1;
     }
+    CKL(cudaEventRecord(L.ev[7], st));
+    cudaStream_t sh = L.stream_hi;
+    CKL(cudaStreamWaitEvent(sh, L.ev[7], 0));
+    FCX_LAUNCH(k_cns_dp, (nb + CDP_THREADS - 1) / CDP_THREADS, CDP_THREADS, 0, sh,
+        L.d_blocks.as<BlockDesc>(), nb, L.d_vmeta.as<VoteMeta>(), L.d_slots.as<uint2>(), L.d_ovf.as<uint2>(),
+        L.d_recs.as<CnsRec>(), L.d_lvl.as<int32_t>(), L.d_cns.as<char>(), L.d_eqv.as<int32_t>(),
+        ctx->want_eqv ? 1 : 0, min_cov, L.d_cnsout.as<CnsOut>());
     CKL(cudaGetLastError());
     L.counters[FCX_C_KERNEL_LAUNCHES] += 1;
     CKL(cudaEventRecord(L.ev[6], sh));
@@ -541,7 +552,14 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
         CKL(L.h_eqv.reserve(cns_total * 4));
         CKL(cudaMemcpyAsync(L.h_eqv.p, L.d_eqv.p, cns_total * 4, cudaMemcpyDeviceToHost, sh));
     }
+    int vote_err = 0;
+    CKL(cudaMemcpyAsync(&vote_err, L.d_counter.as<int>() + 5, 4, cudaMemcpyDeviceToHost, sh));
     CKL(cudaStreamSynchronize(sh));
+    if (vote_err) {
+        L.err = vote_err == 1 ? "consensus vote: more than 160 distinct links at one seed position"
+                              : "consensus vote: link overflow arena exhausted";
+        return vote_err == 2 ? 101 : 3;
+    }
 
     // ---- collect
     const CnsOut* co = L.h_cnsout.as<CnsOut>();
@@ -552,18 +570,17 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
     for (uint32_t b = 0; b < nb; b++) {
         if (co[b].err) {
             char buf[256];
-            snprintf(buf, sizeof buf, "consensus kernel error %d in block %u (1: link table overflow, 2: record overflow, 3: no best score (reference asserts, falcon.c:476))",
+            snprintf(buf, sizeof buf, "consensus kernel error %d in block %u (2: record overflow, 3: no best score (reference asserts, falcon.c:476))",
                      co[b].err, b0 + b);
-            L.err = buf; return 3;
+            L.err = buf; return co[b].err == 2 ? 102 : 3;
         }
-        L.prof[0] += co[b].deep_positions; L.prof[1] += co[b].positions;
-        L.prof[2] += (double)co[b].cyc_vote; L.prof[3] += (double)co[b].cyc_dp;
-        L.prof[4] += (double)co[b].cyc_generic; L.prof[5] += (double)co[b].cyc_backtrack;
-        res.bases.insert(res.bases.end(), hc + hb[b].cns_off, hc + hb[b].cns_off + co[b].len);
+        L.prof[1] += co[b].positions;
+        const uint64_t at = hb[b].cns_off + (uint64_t)co[b].start;       // written back to front (k_cns_dp)
+        res.bases.insert(res.bases.end(), hc + at, hc + at + co[b].len);
         res.lens.push_back((uint64_t)co[b].len);
         if (ctx->want_eqv) {
             const int32_t* he = L.h_eqv.as<int32_t>();
-            res.eqv.insert(res.eqv.end(), he + hb[b].cns_off, he + hb[b].cns_off + co[b].len);
+            res.eqv.insert(res.eqv.end(), he + at, he + at + co[b].len);
         }
     }
     const PairAln* hal = L.h_aln.as<PairAln>();
@@ -636,7 +653,7 @@ extern "C" int fcx_consensus_blocks(fcx_ctx* ctx, uint32_t n_blocks, const uint3
             int slen = ctx->h_len[read_ids[lo]];
             const double mdiff = std::max(0.0, 1.0 - min_idt);
             const double capfrac = std::min(0.3, mdiff < 1.999 ? mdiff / (2.0 - mdiff) : 0.3);
-            double bb = (double)KTAB * 4 + (double)slen * (4 + (8 + (hi - lo - 1) / 16) * 12 + 2 * 5) + 4.0 * slen * (((hi - lo - 1) + 31) & ~31u);
+            double bb = (double)KTAB * 4 + (double)slen * (4 + (8 + (hi - lo - 1) / 16) * 12 + 2 * 5 + 16.0 * VSLOT * 1.5) + 4.0 * CDP_LEVELS * 5 * 4;
             for (uint32_t i = lo + 1; i < hi; i++) {
                 // typical aligned span ~ 0.65 x the shorter sequence (exact sizes follow k_range;
                 // an under-estimate is caught by the out-of-memory split below)
@@ -660,6 +677,15 @@ extern "C" int fcx_consensus_blocks(fcx_ctx* ctx, uint32_t n_blocks, const uint3
     std::function<int(Lane&, uint32_t, uint32_t, WaveResult&)> run_split =
         [&](Lane& L, uint32_t b0, uint32_t b1, WaveResult& out) -> int {
         int rc = run_wave(ctx, L, b0, b1, block_off, read_ids, min_cov, min_idt, out);
+        // capacity heuristics (vote overflow arena, consensus records) are retried with doubled
+        // sizes: the reference reallocs, so a deep or noisy block must not fail the call
+        for (int tries = 0; (rc == 101 || rc == 102) && tries < 6; tries++) {
+            if (rc == 101) L.ovf_scale *= 2; else L.rec_scale *= 2;
+            out = WaveResult(); L.err.clear();
+            rc = run_wave(ctx, L, b0, b1, block_off, read_ids, min_cov, min_idt, out);
+        }
+        L.ovf_scale = L.rec_scale = 1;
+        if (rc == 101 || rc == 102) return 3;
         if (rc != 100) return rc;
         if (b1 - b0 <= 1) { L.err = "a single seed block does not fit in device memory"; return 1; }
         out = WaveResult();

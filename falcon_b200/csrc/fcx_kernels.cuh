@@ -50,9 +50,9 @@ struct BlockDesc {
     uint32_t n_pairs;     // n_seq - 1
     int32_t  slen;        // seed length
     uint32_t rec_cap;     // capacity (records)
-    uint64_t m_off;       // offset (entries) of this block's position-major pile-up matrix
-    uint32_t rb_pad;      // row length of the matrix: n_pairs rounded up to 32
-    uint32_t tile_begin;  // first 32x32 transpose tile of this block
+    uint64_t slot_off;    // offset (positions) of this block's vote slots
+    uint32_t pad_;
+    uint32_t tile_begin;  // first k_vote tile (VOTE_TP positions) of this block
 };
 
 struct PairDesc {
@@ -82,6 +82,9 @@ struct PairAln {          // output of k_dp / k_traceback
     int32_t n_tags;
     int32_t cells;
 };
+
+// per pair, written by k_traceback for accepted pairs (all-zero = not accepted): what k_vote needs
+struct VoteMeta { uint64_t ent_off; uint64_t q_woff; int32_t t_start, t_cnt, q_s, pad; };
 
 // ------------------------------------------------------------------------------ helpers
 __device__ __forceinline__ uint32_t fetch16(const uint32_t* __restrict__ w, int pos) {
@@ -741,7 +744,7 @@ __global__ void k_traceback(const BlockDesc* __restrict__ blocks, const PairDesc
                             uint32_t n_pairs, const uint32_t* __restrict__ pool,
                             const uint32_t* __restrict__ trace_arena, uint32_t* __restrict__ path_arena,
                             uint32_t* __restrict__ xam_arena, uint32_t* __restrict__ ent_arena,
-                            PairAln* __restrict__ aln) {
+                            VoteMeta* __restrict__ vmeta, PairAln* __restrict__ aln) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_pairs) return;
     PairAln a = aln[p];
@@ -849,6 +852,8 @@ __global__ void k_traceback(const BlockDesc* __restrict__ blocks, const PairDesc
     a.t_cnt = t_cnt;
     a.n_tags = t_cnt + (x - n_match_cols);            // target columns + query-only columns among them
     aln[p] = a;
+    VoteMeta vm; vm.ent_off = al.xam_off; vm.q_woff = pd.read_woff; vm.t_start = rg.s2; vm.t_cnt = t_cnt; vm.q_s = rg.s1; vm.pad = 0;
+    vmeta[p] = vm;                                    // (zero = "not accepted" for every other pair)
 }
 
 // query index x at target column y of one read: nearest explicitly recorded column at or before y
@@ -976,57 +981,6 @@ __global__ void k_align1_tb(const uint32_t* __restrict__ pool, uint64_t q_woff, 
     q_aln[pos] = 0; t_aln[pos] = 0;
 }
 
-// ------------------------------------------------------------------------------ k_transpose
-// Per-read entry arrays (read-major, written sequentially by k_traceback) -> per-block
-// position-major pile-up matrix M[i][j] (i = seed position, j = pair index in the block, row
-// length rb_pad) so that k_consensus reads one coalesced 128-byte row segment per 32 reads and
-// position.  Entries outside a read's tagged range, of rejected pairs and of the padding are 0.
-// One warp per 32x32 tile through a padded shared-memory tile; reads and writes are coalesced.
-constexpr int TR_WARPS = 4;
-__global__ void __launch_bounds__(TR_WARPS * 32)
-k_transpose(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, uint32_t n_tiles,
-            const PairRange* __restrict__ ranges, const PairAlloc* __restrict__ allocs,
-            const PairAln* __restrict__ aln, const uint32_t* __restrict__ ent_arena,
-            uint32_t* __restrict__ m_arena) {
-    __shared__ uint32_t tile[TR_WARPS][32][33];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const uint32_t T = blockIdx.x * TR_WARPS + wib;
-    if (T >= n_tiles) return;
-    uint32_t lo = 0, hi = n_blocks;                 // last block with tile_begin <= T
-    while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (blocks[mid].tile_begin <= T) lo = mid; else hi = mid; }
-    const BlockDesc bd = blocks[lo];
-    const uint32_t tl = T - bd.tile_begin;
-    const uint32_t jt = bd.rb_pad >> 5;             // tiles per row
-    const int i0 = (int)(tl / jt) * 32, j0 = (int)(tl % jt) * 32;
-    // lane r owns read j0 + r for the metadata
-    int my_ts = 0, my_cnt = 0; uint64_t my_off = 0;
-    {
-        const uint32_t j = (uint32_t)j0 + lane;
-        if (j < bd.n_pairs) {
-            const uint32_t p = bd.pair_begin + j;
-            const PairAln a = aln[p];
-            if (a.accepted > 0) { my_ts = ranges[p].s2; my_cnt = a.t_cnt; my_off = allocs[p].xam_off; }
-        }
-    }
-    const int i = i0 + lane;
-#pragma unroll 4
-    for (int r = 0; r < 32; r++) {
-        const int ts = __shfl_sync(FULL, my_ts, r), cnt = __shfl_sync(FULL, my_cnt, r);
-        const uint64_t off = __shfl_sync(FULL, my_off, r);
-        const int y = i - ts;
-        uint32_t v = 0;
-        if (y >= 0 && y < cnt) v = ent_arena[off + y];
-        tile[wib][r][lane] = v;
-    }
-    __syncwarp();
-    uint32_t* M = m_arena + bd.m_off;
-#pragma unroll 4
-    for (int c = 0; c < 32; c++) {
-        const int ii = i0 + c;
-        if (ii < bd.slen) M[(size_t)ii * bd.rb_pad + j0 + lane] = tile[wib][lane][c];
-    }
-}
-
 }  // namespace fcx
 
-#include "fcx_consensus.cuh"
+#include "fcx_vote.cuh"

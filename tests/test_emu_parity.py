@@ -76,3 +76,47 @@ def test_round1_dp_kernel_still_agrees(oracle, variant):
     e = emu_engine()
     e.set_option("dp_variant", variant)
     G._check_set(e, oracle, synth.make_set(30000, 2500, 14, seed=9, n_blocks=2), min_cov=3)
+
+
+def test_deep_coverage_overflows_the_position_slots(emu, oracle):
+    """~300 reads over a 2 kb seed: far more than 15 distinct links per position, so links spill to
+    the overflow arena, and more than 256 pairs per block."""
+    S = synth.make_set(20000, 2000, 330, seed=41, n_blocks=1, block_stride=250, max_n_read=500, min_ovl=200)
+    assert len(S.blocks[0]) > 250
+    emu.upload_pool(S.pool)
+    got = emu.consensus_blocks([S.blocks[0].tolist()], 6, 0.70)[0]
+    assert got == oracle.generate_consensus(S.block_seqs(0), 6, 0.70)
+
+
+def test_eqv_and_legacy_symbol(emu, oracle):
+    """generate_consensus(char**, ...) of the emulator library, including the eqv array."""
+    import ctypes as C
+    lib = emu._lib
+    S = synth.make_set(30000, 3000, 20, seed=9, n_blocks=2)
+    for bi in range(2):
+        seqs = S.block_seqs(bi)
+        arr = (C.c_char_p * len(seqs))(*seqs)
+        p = lib.generate_consensus(arr, len(seqs), 4, 8, 0.70)
+        cns = C.string_at(p[0].sequence)
+        eqv = [C.cast(p[0].eff_cov, C.POINTER(C.c_int))[i] for i in range(len(cns))]
+        lib.free_consensus_data(p)
+        want, weqv = oracle.generate_consensus(seqs, 4, 0.70, want_eqv=True)
+        assert cns == want
+        assert eqv == weqv
+
+
+def test_waves_and_capacity_retry(oracle):
+    """Tiny waves, a simulated out-of-memory split and a forced capacity retry give the same bytes."""
+    import os
+    S = synth.make_set(40000, 3000, 18, seed=12, n_blocks=7)
+    e1 = emu_engine()
+    e1.upload_pool(S.pool)
+    blocks = [b.tolist() for b in S.blocks]
+    a = e1.consensus_blocks(blocks, 4, 0.70)
+    e1.set_option("debug_split_above", 2)
+    assert e1.consensus_blocks(blocks, 4, 0.70) == a and e1.stats()["waves"] >= 4
+    e1.set_option("debug_split_above", 0)
+    e1.set_option("debug_tiny_capacity", 1)       # first attempt of every wave overflows its arenas
+    assert e1.consensus_blocks(blocks, 4, 0.70) == a
+    for bi in (0, 6):
+        assert a[bi] == oracle.generate_consensus(S.block_seqs(bi), 4, 0.70)
