@@ -57,7 +57,7 @@ struct Lane {                 // one in-flight wave: stream, events, buffers, st
     cudaStream_t stream_hi = nullptr;   // high priority: the latency-bound consensus kernel
     cudaEvent_t ev[8] = {nullptr};
     DevBuf d_blocks, d_pairs, d_ranges, d_allocs, d_aln, d_ktab, d_kpos, d_trace, d_path, d_xam, d_ent, d_slots,
-           d_ovf, d_vmeta, d_rlist, d_recs, d_lvl, d_cns, d_eqv, d_cnsout, d_counter;
+           d_ovf, d_vmeta, d_rlist, d_recs, d_lvl, d_cns, d_eqv, d_cnsout, d_counter, d_tbhist, d_order, d_kbits;
     HostBuf h_ranges, h_aln, h_cns, h_cnsout, h_eqv;
     std::string err;
     double times[FCX_T_COUNT] = {0};
@@ -68,7 +68,7 @@ struct Lane {                 // one in-flight wave: stream, events, buffers, st
     void release() {
         DevBuf* bufs[] = {&d_blocks, &d_pairs, &d_ranges, &d_allocs, &d_aln, &d_ktab, &d_kpos, &d_trace, &d_path,
                           &d_xam, &d_ent, &d_slots, &d_ovf, &d_vmeta, &d_rlist, &d_recs, &d_lvl, &d_cns, &d_eqv, &d_cnsout,
-                          &d_counter};
+                          &d_counter, &d_tbhist, &d_order, &d_kbits};
         for (auto* b : bufs) b->release();
         HostBuf* hb[] = {&h_ranges, &h_aln, &h_cns, &h_cnsout, &h_eqv};
         for (auto* b : hb) b->release();
@@ -204,7 +204,7 @@ extern "C" int fcx_create(int device, fcx_ctx** out) {
         if (!getenv("FCX_ARENA_GB")) ctx->arena_budget = std::min(ctx->arena_budget, (size_t)((double)free_b * 0.70));
     }
     CKC(cudaFuncSetAttribute(k_range, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             RANGE_WARPS * RANGE_BINS * (int)sizeof(int)));
+                             (KTAB / 32) * 4 + RANGE_WARPS * RANGE_BINS * (int)sizeof(int)));
     ctx->lanes.resize(ctx->n_lanes);
     int prio_lo = 0, prio_hi = 0;
     CKC(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
@@ -423,7 +423,9 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
     // ---- index
     CKL(cudaEventRecord(L.ev[0], st));
     CKL(cudaMemsetAsync(L.d_ktab.p, 0, (size_t)nb * KTAB * 4, st));
-    FCX_LAUNCH(k_index, nb, 256, 0, st, L.d_blocks.as<BlockDesc>(), pool, L.d_ktab.as<uint32_t>(), L.d_kpos.as<uint32_t>());
+    CKR(L.d_kbits.reserve((size_t)nb * (KTAB / 32) * 4));
+    FCX_LAUNCH(k_index, nb, 256, 0, st, L.d_blocks.as<BlockDesc>(), pool, L.d_ktab.as<uint32_t>(), L.d_kpos.as<uint32_t>(),
+               L.d_kbits.as<uint32_t>());
     CKL(cudaGetLastError());
     CKL(cudaEventRecord(L.ev[1], st));
     L.counters[FCX_C_KERNEL_LAUNCHES] += 1;
@@ -431,13 +433,13 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
     if (np) {
         // histogram bins actually needed by this wave (diagonal range <= read + seed length)
         const int bins = std::min(RANGE_BINS, (max_rlen + max_slen) / BIN_SIZE + 8);
-        const size_t rsmem = (size_t)RANGE_WARPS * bins * sizeof(int);
+        const size_t rsmem = (size_t)(KTAB / 32) * 4 + (size_t)RANGE_WARPS * bins * sizeof(int);
         const unsigned per_sm = (unsigned)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / std::max<size_t>(rsmem, 1)));
-        const unsigned rgrid = std::min<unsigned>((np + RANGE_WARPS - 1) / RANGE_WARPS, (unsigned)ctx->sm_count * per_sm);
-        CKR(L.d_rlist.reserve((size_t)rgrid * RANGE_WARPS * RANGE_LIST_CAP * sizeof(int2)));
-        FCX_LAUNCH(k_range, rgrid, RANGE_WARPS * 32, rsmem, st, 
-            L.d_blocks.as<BlockDesc>(), L.d_pairs.as<PairDesc>(), np, pool, L.d_ktab.as<uint32_t>(),
-            L.d_kpos.as<uint32_t>(), L.d_rlist.as<int2>(), bins, L.d_ranges.as<PairRange>());
+        const unsigned rgrid = std::min<unsigned>(nb, (unsigned)ctx->sm_count * per_sm);
+        CKR(L.d_rlist.reserve((size_t)rgrid * RANGE_WARPS * RANGE_LIST_CAP * sizeof(uint32_t)));
+        FCX_LAUNCH(k_range, rgrid, RANGE_WARPS * 32, rsmem, st,
+            L.d_blocks.as<BlockDesc>(), nb, L.d_pairs.as<PairDesc>(), pool, L.d_ktab.as<uint32_t>(),
+            L.d_kpos.as<uint32_t>(), L.d_kbits.as<uint32_t>(), L.d_rlist.as<uint32_t>(), bins, L.d_ranges.as<PairRange>());
         CKL(cudaGetLastError());
         L.counters[FCX_C_KERNEL_LAUNCHES] += 1;
         CKL(cudaMemcpyAsync(L.h_ranges.p, L.d_ranges.p, (size_t)np * sizeof(PairRange), cudaMemcpyDeviceToHost, st));
@@ -514,12 +516,22 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
         CKL(cudaGetLastError());
         L.counters[FCX_C_KERNEL_LAUNCHES] += 1;
         CKL(cudaMemsetAsync(L.d_vmeta.p, 0, (size_t)np * sizeof(VoteMeta), st));
+        // accepted pairs ordered by dist (longest first): warps of k_traceback walk paths of similar length
+        CKR(L.d_tbhist.reserve((TB_BUCKETS + 8) * 4));
+        CKR(L.d_order.reserve((size_t)np * 4));
+        CKL(cudaMemsetAsync(L.d_tbhist.p, 0, (TB_BUCKETS + 8) * 4, st));
+        FCX_LAUNCH(k_tb_hist, (np + 255) / 256, 256, 0, st, L.d_aln.as<PairAln>(), np, L.d_tbhist.as<uint32_t>());
+        FCX_LAUNCH(k_tb_scan, 1, 1024, 0, st, L.d_tbhist.as<uint32_t>());
+        FCX_LAUNCH(k_tb_scatter, (np + 255) / 256, 256, 0, st, L.d_aln.as<PairAln>(), np, L.d_tbhist.as<uint32_t>(),
+                   L.d_order.as<uint32_t>());
+        CKL(cudaGetLastError());
         FCX_LAUNCH(k_traceback, (np + 127) / 128, 128, 0, st,
             L.d_blocks.as<BlockDesc>(), L.d_pairs.as<PairDesc>(), L.d_ranges.as<PairRange>(),
-            L.d_allocs.as<PairAlloc>(), np, pool, L.d_trace.as<uint32_t>(), L.d_path.as<uint32_t>(),
+            L.d_allocs.as<PairAlloc>(), L.d_order.as<uint32_t>(), L.d_tbhist.as<uint32_t>() + TB_BUCKETS, pool,
+            L.d_trace.as<uint32_t>(), L.d_path.as<uint32_t>(),
             L.d_xam.as<uint32_t>(), L.d_ent.as<uint32_t>(), L.d_vmeta.as<VoteMeta>(), L.d_aln.as<PairAln>());
         CKL(cudaGetLastError());
-        L.counters[FCX_C_KERNEL_LAUNCHES] += 1;
+        L.counters[FCX_C_KERNEL_LAUNCHES] += 4;
     }
     CKL(cudaEventRecord(L.ev[5], st));
     // ---- consensus: the column vote (parallel over positions), then the serial longest-path DP and

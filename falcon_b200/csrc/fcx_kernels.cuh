@@ -147,21 +147,29 @@ __global__ void k_pack(const uint8_t* __restrict__ ascii, const uint64_t* __rest
 __global__ void __launch_bounds__(256) k_index(const BlockDesc* __restrict__ blocks,
                                                const uint32_t* __restrict__ pool,
                                                uint32_t* __restrict__ ktab,
-                                               uint32_t* __restrict__ kpos_arena) {
+                                               uint32_t* __restrict__ kpos_arena,
+                                               uint32_t* __restrict__ kbits) {
     const BlockDesc bd = blocks[blockIdx.x];
     const uint32_t* seed = pool + bd.seed_woff;
     uint32_t* tab = ktab + (size_t)blockIdx.x * KTAB;
     uint32_t* kpos = kpos_arena + bd.kpos_off;
     const int n = bd.slen - KMER;
     const int tid = threadIdx.x;
-    if (n <= 0) return;
+    // bitmap of the non-empty buckets (8 KB per seed): k_range keeps it in shared memory and only
+    // goes to the 256 KB table for the ~1 in 4 query k-mers that can have a hit
+    uint32_t* bits = kbits + (size_t)blockIdx.x * (KTAB / 32);
+    if (n <= 0) { for (int j = tid; j < KTAB / 32; j += 256) bits[j] = 0u; return; }
     for (int i = tid; i < n; i += 256) atomicAdd(&tab[fetch16(seed, i) & 0xffffu], 1u);
     __syncthreads();
     // exclusive scan, 256 entries per thread
     __shared__ uint32_t part[256];
     uint32_t sum = 0;
     uint32_t* mine = tab + tid * 256;
-    for (int j = 0; j < 256; j++) sum += mine[j];
+    for (int w = 0; w < 8; w++) {
+        uint32_t bw = 0;
+        for (int j = 0; j < 32; j++) { const uint32_t c = mine[w * 32 + j]; sum += c; bw |= (c ? 1u : 0u) << j; }
+        bits[tid * 8 + w] = bw;
+    }
     part[tid] = sum;
     __syncthreads();
     if (tid == 0) { uint32_t run = 0; for (int j = 0; j < 256; j++) { uint32_t v = part[j]; part[j] = run; run += v; } }
@@ -334,23 +342,36 @@ __device__ void range_pair_slow(const uint32_t* __restrict__ read, const uint32_
 // one scratch slot and loops over pairs.
 constexpr int RANGE_LIST_CAP = 16384;
 
+// A match (query position i = 0, 4, 8, ... < 100000, seed position t < 100000) packed in 32 bits
+__device__ __forceinline__ uint32_t rm_pack(int i, int t) { return ((uint32_t)(i >> 2) << 17) | (uint32_t)t; }
+__device__ __forceinline__ int rm_q(uint32_t m) { return (int)(m >> 17) << 2; }
+__device__ __forceinline__ int rm_t(uint32_t m) { return (int)(m & 0x1ffffu); }
+
+// Persistent CTAs, one seed block at a time: the block's non-empty-bucket bitmap (8 KB, from k_index)
+// sits in shared memory, its 256 KB bucket table and position list stay hot in L1/L2 because all
+// pairs of the block are looked up back to back by the four warps of one CTA.
 __global__ void __launch_bounds__(RANGE_WARPS * 32)
-k_range(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs, uint32_t n_pairs,
+k_range(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, const PairDesc* __restrict__ pairs,
         const uint32_t* __restrict__ pool, const uint32_t* __restrict__ ktab,
-        const uint32_t* __restrict__ kpos_arena, int2* __restrict__ list_scratch, int bins,
-        PairRange* __restrict__ out) {
-    FCX_DYN_SHARED(int, s_hist_all);
+        const uint32_t* __restrict__ kpos_arena, const uint32_t* __restrict__ kbits,
+        uint32_t* __restrict__ list_scratch, int bins, PairRange* __restrict__ out) {
+    FCX_DYN_SHARED(int, s_dyn_all);
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    int* hist = s_hist_all + wib * bins;      // bins >= (max read len + max seed len) / 48 + 2 for this wave
-    const uint32_t gw = blockIdx.x * RANGE_WARPS + wib, nw = gridDim.x * RANGE_WARPS;
-    int2* list = list_scratch + (size_t)gw * RANGE_LIST_CAP;
+    uint32_t* sbits = reinterpret_cast<uint32_t*>(s_dyn_all);                 // KTAB / 32 words
+    int* hist = s_dyn_all + KTAB / 32 + wib * bins;      // bins >= (max read len + max seed len) / 48 + 2 for this wave
+    const uint32_t gw = blockIdx.x * RANGE_WARPS + wib;
+    uint32_t* list = list_scratch + (size_t)gw * RANGE_LIST_CAP;
     const unsigned lt = lanemask_lt();
-    for (uint32_t p = gw; p < n_pairs; p += nw) {
+  for (uint32_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+    const BlockDesc bd = blocks[blk];
+    __syncthreads();                                     // every warp is done with the previous bitmap
+    for (int j = threadIdx.x; j < KTAB / 32; j += RANGE_WARPS * 32) sbits[j] = __ldg(kbits + (size_t)blk * (KTAB / 32) + j);
+    __syncthreads();
+    const uint32_t* tab = ktab + (size_t)blk * KTAB;
+    const uint32_t* kpos = kpos_arena + bd.kpos_off;
+    for (uint32_t p = bd.pair_begin + wib; p < bd.pair_begin + bd.n_pairs; p += RANGE_WARPS) {
         const PairDesc pd = pairs[p];
-        const BlockDesc bd = blocks[pd.block];
         const uint32_t* read = pool + pd.read_woff;
-        const uint32_t* tab = ktab + (size_t)pd.block * KTAB;
-        const uint32_t* kpos = kpos_arena + bd.kpos_off;
         const int nq = pd.rlen > KMER ? (pd.rlen - KMER + 3) / 4 : 0;   // i = 0,4,.. < rlen-K
         PairRange r; r.s1 = r.e1 = r.s2 = r.e2 = 0; r.n_match = 0; r.pass = 0;
         // ---- materialise the match list
@@ -360,7 +381,7 @@ k_range(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs
             uint32_t s = 0, e = 0;
             if (it < nq) {
                 const uint32_t kid = fetch16(read, i) & 0xffffu;
-                s = kid ? __ldg(tab + kid - 1) : 0u; e = __ldg(tab + kid);
+                if ((sbits[kid >> 5] >> (kid & 31)) & 1u) { s = kid ? __ldg(tab + kid - 1) : 0u; e = __ldg(tab + kid); }
             }
             const int c = (int)(e - s);
             int incl = c;
@@ -371,7 +392,7 @@ k_range(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs
             int w = n + incl - c;
             for (uint32_t j = s; j < e; j++, w++) {
                 const int t = (int)__ldg(kpos + j);
-                list[w] = make_int2(i, t);
+                list[w] = rm_pack(i, t);
                 dmin = min(dmin, i - t); dmax = max(dmax, i - t);
             }
             n += total;
@@ -386,7 +407,7 @@ k_range(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs
         // ---- histogram (kmer_lookup.c:346-355)
         for (int e0 = 0; e0 < n; e0 += 32) {
             const int e = e0 + lane;
-            if (e < n) { const int2 m = list[e]; atomicAdd(&hist[(m.x - m.y - dmin) / BIN_SIZE], 1); }
+            if (e < n) { const uint32_t m = list[e]; atomicAdd(&hist[(rm_q(m) - rm_t(m) - dmin) / BIN_SIZE], 1); }
         }
         __syncwarp();
         int top = 0;
@@ -397,7 +418,7 @@ k_range(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs
         int top_bin = -1;
         for (int e0 = 0; e0 < n && top_bin < 0; e0 += 32) {
             const int e = e0 + lane; int mybin = -1;
-            if (e < n) { const int2 m = list[e]; const int b = (m.x - m.y - dmin) / BIN_SIZE; if (hist[b] == top) mybin = b; }
+            if (e < n) { const uint32_t m = list[e]; const int b = (rm_q(m) - rm_t(m) - dmin) / BIN_SIZE; if (hist[b] == top) mybin = b; }
             const unsigned bal = __ballot_sync(FULL, mybin >= 0);
             if (bal) top_bin = __shfl_sync(FULL, mybin, __ffs(bal) - 1);
         }
@@ -410,7 +431,7 @@ k_range(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs
             const int e = e0 + lane;
             bool keep = false; int qi = 0, ti = 0;
             if (e < n) {
-                const int2 m = list[e]; qi = m.x; ti = m.y;
+                const uint32_t m = list[e]; qi = rm_q(m); ti = rm_t(m);
                 const int b = (qi - ti - dmin) / BIN_SIZE;
                 keep = abs(b - top_bin) <= 5 && hist[b] > COUNT_TH;
             }
@@ -452,6 +473,7 @@ k_range(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs
         if (lane == 0) out[p] = r;
         __syncwarp();
     }
+  }
 }
 
 // ------------------------------------------------------------------------------ k_dp
@@ -739,16 +761,56 @@ constexpr int ENT_INS_INLINE = 11;
 __device__ __forceinline__ int ent_nins(uint32_t e) { return (int)((e >> 22) & 0xffu); }
 __device__ __forceinline__ int ent_ins(uint32_t e, int k) { return (int)((e >> (2 * k)) & 3u); }
 
-__global__ void k_traceback(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs,
-                            const PairRange* __restrict__ ranges, const PairAlloc* __restrict__ allocs,
-                            uint32_t n_pairs, const uint32_t* __restrict__ pool,
-                            const uint32_t* __restrict__ trace_arena, uint32_t* __restrict__ path_arena,
-                            uint32_t* __restrict__ xam_arena, uint32_t* __restrict__ ent_arena,
-                            VoteMeta* __restrict__ vmeta, PairAln* __restrict__ aln) {
+// Work ordering for k_traceback: accepted pairs bucketed by dist (32 steps per bucket, longest
+// first), so that the 32 threads of a warp walk paths of similar length.  Three tiny kernels:
+// histogram, exclusive scan, scatter.  The order inside a bucket is arbitrary (atomics); results do
+// not depend on it.
+constexpr int TB_BUCKETS = 2048;
+__device__ __forceinline__ int tb_bucket(int dist) { return TB_BUCKETS - 1 - min(dist >> 5, TB_BUCKETS - 1); }
+
+__global__ void k_tb_hist(const PairAln* __restrict__ aln, uint32_t n_pairs, uint32_t* __restrict__ hist) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_pairs) return;
+    const PairAln a = aln[p];
+    if (a.accepted > 0) atomicAdd(&hist[tb_bucket(a.dist)], 1u);
+}
+// one CTA of 1024 threads, two buckets each; hist[] becomes the exclusive scan, hist[TB_BUCKETS] the total
+__global__ void __launch_bounds__(1024) k_tb_scan(uint32_t* __restrict__ hist) {
+    __shared__ uint32_t part[1024];
+    const int t = threadIdx.x;
+    const uint32_t a = hist[2 * t], b = hist[2 * t + 1];
+    part[t] = a + b;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const uint32_t v = t >= o ? part[t - o] : 0u;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    const uint32_t excl = part[t] - (a + b);
+    hist[2 * t] = excl; hist[2 * t + 1] = excl + a;
+    if (t == 1023) hist[TB_BUCKETS] = part[t];
+}
+__global__ void k_tb_scatter(const PairAln* __restrict__ aln, uint32_t n_pairs, uint32_t* __restrict__ cursor,
+                             uint32_t* __restrict__ order) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pairs) return;
+    const PairAln a = aln[p];
+    if (a.accepted > 0) order[atomicAdd(&cursor[tb_bucket(a.dist)], 1u)] = p;
+}
+
+__global__ void __launch_bounds__(128)
+k_traceback(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs,
+            const PairRange* __restrict__ ranges, const PairAlloc* __restrict__ allocs,
+            const uint32_t* __restrict__ order, const uint32_t* __restrict__ n_order,
+            const uint32_t* __restrict__ pool,
+            const uint32_t* __restrict__ trace_arena, uint32_t* __restrict__ path_arena,
+            uint32_t* __restrict__ xam_arena, uint32_t* __restrict__ ent_arena,
+            VoteMeta* __restrict__ vmeta, PairAln* __restrict__ aln) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= *n_order) return;
+    const uint32_t p = order[slot];
     PairAln a = aln[p];
-    if (a.accepted <= 0) return;
     const PairRange rg = ranges[p];
     const PairDesc pd = pairs[p];
     const uint32_t* q = pool + pd.read_woff;
@@ -785,9 +847,12 @@ __global__ void k_traceback(const BlockDesc* __restrict__ blocks, const PairDesc
     for (; d >= 1; d--) step_back(d, __ldg(reinterpret_cast<const uint2*>(trace + (size_t)d * TRACE_REC_WORDS)));
     // (2) forwards.  ent[] was pre-filled with ENT_PLAIN (= a match column without insertions), so
     // only the other columns are written: target-only columns and columns followed by query-only
-    // columns.  xam[] (query index at the column, used by the rare generic consensus path to fetch
-    // inserted bases beyond the 11 inline ones) is written at exactly those columns and at y = 0;
+    // columns.  xam[] (query index at the column, used by the consensus vote to fetch inserted
+    // bases beyond the 11 inline ones) is written at exactly those columns and at y = 0;
     // xam_lookup() reconstructs it anywhere else.
+    // The loop body is one straight-line "step": the indel of step d, then ONE 16-base compare
+    // (longer snakes are rare and finish in a small loop), all state updates by selects, so that
+    // the 32 pairs of a warp (ordered by dist) stay converged.
     int x = 0, y = 0, run = 0, t_cnt = -1, n_match_cols = 0;
     uint32_t pend = 0; int pend_y = -1, pend_x = 0;   // entry of the last target column, still open
     uint32_t pw = 0;
@@ -805,49 +870,46 @@ __global__ void k_traceback(const BlockDesc* __restrict__ blocks, const PairDesc
         if (wi != wt_i) { wt_i = wi; wt_lo = __ldg(t + wi); wt_hi = __ldg(t + wi + 1); }
         return __funnelshift_r(wt_lo, wt_hi, (pos & 15) << 1);
     };
+    auto flush = [&]() {          // store the open entry unless it is a plain match column
+        if (pend_y >= 0 && (run > 0 || !(pend & ENT_MATCH))) {
+            ent[pend_y] = pend | ((uint32_t)run << 22);
+            xam[pend_y] = ((uint32_t)pend_x << 1) | ((pend & ENT_MATCH) ? 1u : 0u);
+        }
+    };
     for (int d = 0; d <= D; d++) {
         if (d > 0) {
             if ((d & 31) == 0 || d == 1) pw = path[d >> 5];
-            if ((pw >> (d & 31)) & 1u) {              // target-only column
-                if (pend_y >= 0 && (run > 0 || !(pend & ENT_MATCH))) {
-                    ent[pend_y] = pend | ((uint32_t)run << 22);
-                    xam[pend_y] = ((uint32_t)pend_x << 1) | ((pend & ENT_MATCH) ? 1u : 0u);
-                }
-                pend = ENT_VALID; pend_y = y; pend_x = x; y++; run = 0;
-            } else {                                  // query-only column
-                if (run < ENT_INS_INLINE) pend |= (win_q(qs + x) & 3u) << (2 * run);
-                x++; run++;
-                if (run == 255) {            // the 255th consecutive query-only column: tags stop before it
-                    t_cnt = y;               // target positions 0..y-1 carry tags
-                    x--; run = 254;          // exactly 254 insertion tags remain on column y-1
-                    break;
-                }
+            const bool del = ((pw >> (d & 31)) & 1u) != 0;          // target-only column
+            const uint32_t qb = win_q(qs + x) & 3u;                  // the query base of a query-only column
+            if (del) flush();
+            const uint32_t ins_bits = run < ENT_INS_INLINE ? qb << (2 * run) : 0u;
+            pend = del ? ENT_VALID : (pend | ins_bits);
+            pend_y = del ? y : pend_y; pend_x = del ? x : pend_x;
+            run = del ? 0 : run + 1;
+            y += del ? 1 : 0; x += del ? 0 : 1;
+            if (run == 255) {            // the 255th consecutive query-only column: tags stop before it
+                t_cnt = y;               // target positions 0..y-1 carry tags
+                x--; run = 254;          // exactly 254 insertion tags remain on column y-1
+                break;
             }
         }
         // snake: no per-base stores, interior match columns stay ENT_PLAIN
-        int adv = 0;
-        for (;;) {
-            int rem = min(q_len - x - adv, t_len - y - adv);
-            if (rem <= 0) break;
-            uint32_t diff = win_q(qs + x + adv) ^ win_t(ts + y + adv);
-            int n = diff ? (__ffs(diff) - 1) >> 1 : 16;
-            n = min(n, rem);
-            adv += n;
-            if (n < 16) break;
+        int rem = min(q_len - x, t_len - y);
+        uint32_t diff = win_q(qs + x) ^ win_t(ts + y);
+        int adv = min((int)((unsigned)(__ffs(diff) - 1) >> 1), max(min(rem, 16), 0));
+        while (adv > 0 && (adv & 15) == 0 && adv < rem) {            // long snake: rare
+            diff = win_q(qs + x + adv) ^ win_t(ts + y + adv);
+            const int nn = min((int)((unsigned)(__ffs(diff) - 1) >> 1), min(rem - adv, 16));
+            adv += nn;
+            if (nn < 16) break;
         }
         if (adv > 0) {
-            if (pend_y >= 0 && (run > 0 || !(pend & ENT_MATCH))) {
-                ent[pend_y] = pend | ((uint32_t)run << 22);
-                xam[pend_y] = ((uint32_t)pend_x << 1) | ((pend & ENT_MATCH) ? 1u : 0u);
-            }
+            flush();
             x += adv; y += adv; n_match_cols += adv;
             pend = ENT_PLAIN; pend_y = y - 1; pend_x = x - 1; run = 0;
         }
     }
-    if (pend_y >= 0 && (run > 0 || !(pend & ENT_MATCH))) {
-        ent[pend_y] = pend | ((uint32_t)run << 22);
-        xam[pend_y] = ((uint32_t)pend_x << 1) | ((pend & ENT_MATCH) ? 1u : 0u);
-    }
+    flush();
     if (t_cnt < 0) t_cnt = y;
     a.t_cnt = t_cnt;
     a.n_tags = t_cnt + (x - n_match_cols);            // target columns + query-only columns among them
