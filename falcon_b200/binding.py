@@ -113,6 +113,19 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
                                          C.POINTER(C.c_void_p)]
     lib.fcx_last_pair_info.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     lib.fcx_last_stats.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+    lib.fcx_multi_create.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]
+    lib.fcx_multi_destroy.argtypes = [C.c_void_p]
+    lib.fcx_multi_last_error.argtypes = [C.c_void_p]
+    lib.fcx_multi_last_error.restype = C.c_char_p
+    lib.fcx_multi_device_count.argtypes = [C.c_void_p]
+    lib.fcx_multi_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+    lib.fcx_multi_pool_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+    lib.fcx_multi_peer_bytes.argtypes = [C.c_void_p]
+    lib.fcx_multi_peer_bytes.restype = C.c_uint64
+    lib.fcx_multi_consensus_blocks.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint, C.c_uint,
+                                               C.c_double, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+    lib.fcx_multi_last_pair_info.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    lib.fcx_multi_last_stats.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     lib.fcx_parser_create.argtypes = [C.c_uint] * 5
     lib.fcx_parser_create.restype = C.c_void_p
     lib.fcx_parser_destroy.argtypes = [C.c_void_p]
@@ -290,6 +303,75 @@ class Engine:
         t = (C.c_double * len(T_NAMES))()
         c = (C.c_uint64 * len(C_NAMES))()
         self._lib.fcx_last_stats(self._h, t, c)
+        d = {"ms_" + k: t[i] for i, k in enumerate(T_NAMES)}
+        d.update({k: int(c[i]) for i, k in enumerate(C_NAMES)})
+        return d
+
+
+class MultiEngine(Engine):
+    """Several GPUs in one process: one read store on every device, seed blocks sharded in
+    contiguous cost-balanced slices, results merged in seed order (fcx_multi_*).
+    Same surface as Engine."""
+
+    def __init__(self, devices: Sequence[int]):
+        self._lib = lib()
+        self._open(devices)
+
+    def _open(self, devices: Sequence[int]):
+        arr = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        if self._lib.fcx_multi_create(arr, len(devices), C.byref(h)) != 0:
+            raise EngineError("fcx_multi_create(%s): %s" % (list(devices), self._lib.fcx_multi_last_error(None).decode()))
+        self._h = h
+        self.devices = list(devices)
+        self.n_reads = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.fcx_multi_destroy(self._h)
+            self._h = None
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise EngineError("%s: %s" % (what, self._lib.fcx_multi_last_error(self._h).decode()))
+
+    def set_option(self, name: str, value: float):
+        self._check(self._lib.fcx_multi_set_option(self._h, name.encode(), float(value)), "fcx_multi_set_option")
+
+    def upload_pool_raw(self, bases_ptr: int, offsets: np.ndarray):
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = offsets.shape[0] - 1
+        self._check(self._lib.fcx_multi_pool_upload(self._h, bases_ptr, offsets.ctypes.data, n), "fcx_multi_pool_upload")
+        self.n_reads = n
+
+    def peer_bytes(self) -> int:
+        return int(self._lib.fcx_multi_peer_bytes(self._h))
+
+    def consensus_blocks_raw(self, block_off: np.ndarray, read_ids: np.ndarray, min_cov: int,
+                             min_idt: float, K: int = 8) -> Tuple[np.ndarray, np.ndarray]:
+        block_off = np.ascontiguousarray(block_off, dtype=np.uint32)
+        read_ids = np.ascontiguousarray(read_ids, dtype=np.uint32)
+        nb = block_off.shape[0] - 1
+        ob, oo = C.c_void_p(), C.c_void_p()
+        self._check(self._lib.fcx_multi_consensus_blocks(self._h, nb, block_off.ctypes.data, read_ids.ctypes.data,
+                                                         min_cov, K, min_idt, C.byref(ob), C.byref(oo)),
+                    "fcx_multi_consensus_blocks")
+        off = np.ctypeslib.as_array((C.c_uint64 * (nb + 1)).from_address(oo.value)).copy()
+        total = int(off[-1])
+        data = np.ctypeslib.as_array((C.c_uint8 * total).from_address(ob.value)).copy() if total else np.zeros(0, dtype=np.uint8)
+        return data, off
+
+    def pair_info(self) -> List[PairInfo]:
+        n = C.c_uint64()
+        self._lib.fcx_multi_last_pair_info(self._h, None, 0, C.byref(n))
+        arr = (PairInfo * max(1, n.value))()
+        self._lib.fcx_multi_last_pair_info(self._h, arr, n.value, C.byref(n))
+        return list(arr)[: n.value]
+
+    def stats(self) -> dict:
+        t = (C.c_double * len(T_NAMES))()
+        c = (C.c_uint64 * len(C_NAMES))()
+        self._lib.fcx_multi_last_stats(self._h, t, c)
         d = {"ms_" + k: t[i] for i, k in enumerate(T_NAMES)}
         d.update({k: int(c[i]) for i, k in enumerate(C_NAMES)})
         return d

@@ -16,6 +16,7 @@ import argparse
 import logging
 import re
 import sys
+import threading
 from typing import Iterator, List, Optional, Sequence, Tuple
 
 LOG = logging.getLogger()
@@ -161,6 +162,21 @@ def _normalise_flags(argv: Sequence[str]) -> List[str]:
     return out
 
 
+def parse_devices(spec: str):
+    """'0-3' / '0,2,5' / '1' -> list of device ordinals."""
+    out = []
+    for part in spec.split(","):
+        part = part.strip()
+        if "-" in part:
+            a, b = part.split("-", 1)
+            out.extend(range(int(a), int(b) + 1))
+        elif part:
+            out.append(int(part))
+    if not out:
+        raise ValueError("--devices: empty device list")
+    return out
+
+
 def parse_args(argv):
     """Same options and defaults as consensus.py:216-251."""
     parser = argparse.ArgumentParser(
@@ -194,6 +210,12 @@ def parse_args(argv):
                         help="logging level (WARNING=3, INFO=2, DEBUG=1)")
     # B200 engine knobs (not in the reference)
     parser.add_argument("--device", type=int, default=None, help="CUDA device ordinal (default: $FCX_DEVICE or 0)")
+    parser.add_argument("--devices", type=str, default=None,
+                        help="several GPUs in this one process, e.g. 0-7 or 0,2,3: one read store on every device, "
+                             "seed blocks sharded across them, output in input order")
+    parser.add_argument("--stream", action="append", default=None, metavar="IN:OUT",
+                        help="read LA4Falcon text from IN and write its FASTA to OUT instead of stdin/stdout; repeat the "
+                             "option to serve several producers (files or named pipes) with this one GPU process")
     parser.add_argument("--batch-blocks", type=int, default=1024, help="seed blocks per GPU batch")
     parser.add_argument("--batch-bases", type=int, default=1 << 30, help="read bases per GPU batch")
     parser.add_argument("--python-parser", action="store_true", default=False,
@@ -260,25 +282,68 @@ def emit(out, cns: str, seed_id: str, args, good_region=re.compile("[ACGT]+")):
         out.write(runs[-1] + "\n")
 
 
-def run_native_parser(args, stdin, stdout, engine):
-    """stdin -> native parser (fcx_parser_*) -> engine, in batches; output in stdin order."""
+def _stream_reader(args, stream_no, fin, q):
+    """Producer thread of one input stream: stdin bytes -> native parser (fcx_parser_*, the GIL is
+    released inside the C calls) -> batches on the queue.  The parser hands out two alternating
+    buffer sets, and the queue holds one batch per stream, so parsing batch n+1 overlaps the GPU
+    work on batch n."""
     from .binding import StreamParser
     ps = StreamParser(args.min_n_read, args.min_len_aln, args.max_n_read, args.min_cov_aln, args.max_cov_aln)
-    done = False
-    while not done:
-        chunk = stdin.read(1 << 24)
-        eof = not chunk
-        pending = ps.feed(chunk or b"", eof)
-        done = eof or ps.stopped
-        while pending >= args.batch_blocks or (done and pending > 0):
-            bases_ptr, offsets, block_off, read_ids, ids = ps.take(args.batch_blocks, args.batch_bases)
-            engine.upload_pool_raw(bases_ptr, offsets)
-            data, off = engine.consensus_blocks_raw(block_off, read_ids, args.min_cov, args.min_idt, K)
-            raw = data.tobytes()
-            for i, sid in enumerate(ids):
-                emit(stdout, raw[int(off[i]):int(off[i + 1])].decode(), sid, args)
-            pending = ps.pending()
-    ps.close()
+    try:
+        done = False
+        while not done:
+            chunk = fin.read(1 << 24)
+            eof = not chunk
+            pending = ps.feed(chunk or b"", eof)
+            done = eof or ps.stopped
+            while pending >= args.batch_blocks or (done and pending > 0):
+                batch = ps.take(args.batch_blocks, args.batch_bases)
+                ev = threading.Event()
+                q.put((stream_no, batch, ev))
+                ev.wait()             # consumed: its buffer set may be overwritten by the take after next
+                pending = ps.pending()
+        q.put((stream_no, None, None))
+    except BaseException as e:  # noqa: BLE001 -- reported by the consumer
+        q.put((stream_no, e, None))
+    # the parser (and the buffers of the last batch) must outlive the consumer: closed by the caller
+    return ps
+
+
+def run_native_parser(args, streams, engine):
+    """LA4Falcon text -> native parser -> engine, in batches; output in input order per stream.
+    `streams` is a list of (binary input file, text output file).  One producer thread per stream
+    parses while this thread drives the GPU(s) and writes the FASTA."""
+    import queue
+    q = queue.Queue(maxsize=max(2, len(streams)))
+    parsers = [None] * len(streams)
+
+    def producer(i):
+        parsers[i] = _stream_reader(args, i, streams[i][0], q)
+
+    threads = [threading.Thread(target=producer, args=(i,), daemon=True) for i in range(len(streams))]
+    for t in threads:
+        t.start()
+    live = len(streams)
+    while live:
+        stream_no, batch, ev = q.get()
+        if batch is None:
+            live -= 1
+            continue
+        if isinstance(batch, BaseException):
+            raise batch
+        bases_ptr, offsets, block_off, read_ids, ids = batch
+        engine.upload_pool_raw(bases_ptr, offsets)
+        ev.set()                      # the read bytes are on the device: the producer may go on
+        data, off = engine.consensus_blocks_raw(block_off, read_ids, args.min_cov, args.min_idt, K)
+        raw = data.tobytes()
+        out = streams[stream_no][1]
+        for i, sid in enumerate(ids):
+            emit(out, raw[int(off[i]):int(off[i + 1])].decode(), sid, args)
+    for t in threads:
+        t.join()
+    for ps in parsers:
+        if ps is not None:
+            ps.close()
 
 
 def run(args, stdin=None, stdout=None, engine=None):
@@ -288,11 +353,31 @@ def run(args, stdin=None, stdout=None, engine=None):
     if engine is None:
         import os
         from .binding import Engine
-        dev = args.device if args.device is not None else int(os.environ.get("FCX_DEVICE", "0"))
-        engine = Engine(dev)
+        devs = parse_devices(args.devices) if getattr(args, "devices", None) else None
+        if devs and len(devs) > 1:
+            from .binding import MultiEngine
+            engine = MultiEngine(devs)
+        else:
+            dev = devs[0] if devs else (args.device if args.device is not None else int(os.environ.get("FCX_DEVICE", "0")))
+            engine = Engine(dev)
     if not args.trim and not args.python_parser and hasattr(engine, "upload_pool_raw"):
-        run_native_parser(args, stdin, stdout, engine)
-        stdout.flush()
+        streams, opened = [(stdin, stdout)], []
+        if getattr(args, "stream", None):
+            # several LA4Falcon producers feeding this one process (which owns the GPUs):
+            # --stream IN:OUT, repeated; IN / OUT are files or named pipes
+            streams = []
+            for spec in args.stream:
+                fin_name, fout_name = spec.split(":", 1)
+                fin, fout = open(fin_name, "rb"), open(fout_name, "w")
+                opened += [fin, fout]
+                streams.append((fin, fout))
+        try:
+            run_native_parser(args, streams, engine)
+        finally:
+            for _, fout in streams:
+                fout.flush()
+            for f in opened:
+                f.close()
         return
     config = (args.min_cov, K, args.max_n_read, args.min_idt, args.edge_tolerance, args.trim_size,
               args.min_cov_aln, args.max_cov_aln)

@@ -45,10 +45,11 @@ struct fcx_parser {
     unsigned long long read_cov = 0;
     std::unordered_set<std::string> ids;
     std::deque<Block> ready;
-    // storage handed out by fcx_parser_take
-    std::vector<char> o_bases, o_ids;
-    std::vector<uint64_t> o_off;
-    std::vector<uint32_t> o_boff, o_rids;
+    // storage handed out by fcx_parser_take: two sets used alternately, so that the batch of the
+    // previous take() stays valid while the caller (another thread) is still consuming it
+    struct Out { std::vector<char> bases, ids; std::vector<uint64_t> off; std::vector<uint32_t> boff, rids; };
+    Out outs[2];
+    unsigned take_no = 0;
 
     void reset_block() {
         cur.seed_id.clear(); cur.data.clear(); cur.reads.clear(); cur.order.clear();
@@ -156,25 +157,26 @@ extern "C" int fcx_parser_stopped(const fcx_parser* ps) { return ps->stopped ? 1
 extern "C" int fcx_parser_take(fcx_parser* ps, uint32_t max_blocks, uint64_t max_bases, const char** bases,
                                const uint64_t** offsets, uint32_t* n_reads, const uint32_t** block_off,
                                const uint32_t** read_ids, uint32_t* n_blocks, const char** seed_ids) {
-    ps->o_bases.clear(); ps->o_ids.clear(); ps->o_off.assign(1, 0); ps->o_boff.assign(1, 0); ps->o_rids.clear();
+    fcx_parser::Out& o = ps->outs[ps->take_no++ & 1u];
+    o.bases.clear(); o.ids.clear(); o.off.assign(1, 0); o.boff.assign(1, 0); o.rids.clear();
     uint32_t nb = 0; uint64_t total = 0;
     while (!ps->ready.empty() && nb < max_blocks) {
         Block& b = ps->ready.front();
         const uint64_t sz = b.data.size();
         if (nb > 0 && total + sz > max_bases) break;
-        const uint32_t base_id = (uint32_t)(ps->o_off.size() - 1);
-        const uint64_t base_off = ps->o_bases.size();
-        ps->o_bases.insert(ps->o_bases.end(), b.data.begin(), b.data.end());      // one copy per block
-        for (auto& r : b.reads) ps->o_off.push_back(base_off + r.off + r.len);
-        for (uint32_t k : b.order) ps->o_rids.push_back(base_id + k);
-        ps->o_boff.push_back((uint32_t)ps->o_rids.size());
-        ps->o_ids.insert(ps->o_ids.end(), b.seed_id.begin(), b.seed_id.end());
-        ps->o_ids.push_back('\0');
+        const uint32_t base_id = (uint32_t)(o.off.size() - 1);
+        const uint64_t base_off = o.bases.size();
+        o.bases.insert(o.bases.end(), b.data.begin(), b.data.end());      // one copy per block
+        for (auto& r : b.reads) o.off.push_back(base_off + r.off + r.len);
+        for (uint32_t k : b.order) o.rids.push_back(base_id + k);
+        o.boff.push_back((uint32_t)o.rids.size());
+        o.ids.insert(o.ids.end(), b.seed_id.begin(), b.seed_id.end());
+        o.ids.push_back('\0');
         total += sz; nb++;
         ps->ready.pop_front();
     }
-    ps->o_bases.push_back('\0');
-    *bases = ps->o_bases.data(); *offsets = ps->o_off.data(); *n_reads = (uint32_t)(ps->o_off.size() - 1);
-    *block_off = ps->o_boff.data(); *read_ids = ps->o_rids.data(); *n_blocks = nb; *seed_ids = ps->o_ids.data();
+    o.bases.push_back('\0');
+    *bases = o.bases.data(); *offsets = o.off.data(); *n_reads = (uint32_t)(o.off.size() - 1);
+    *block_off = o.boff.data(); *read_ids = o.rids.data(); *n_blocks = nb; *seed_ids = o.ids.data();
     return 0;
 }

@@ -182,7 +182,8 @@ int fcx_last_stats(fcx_ctx *, double *times_ms /*FCX_T_COUNT*/, uint64_t *counte
  * blocks queued, or -(queued + 1) once the "- -" terminator has been seen; take() hands out up to
  * max_blocks blocks (and at most max_bases bases, but at least one block) as a pool + block lists
  * in exactly the shape fcx_pool_upload / fcx_consensus_blocks accept; seed_ids are NUL-separated.
- * The returned buffers are owned by the parser and valid until the next take(). */
+ * The returned buffers are owned by the parser and stay valid until the SECOND next take() (two
+ * sets are used alternately, so one thread can parse the next batch while another consumes this one). */
 typedef struct fcx_parser fcx_parser;
 fcx_parser *fcx_parser_create(unsigned min_n_read, unsigned min_len_aln, unsigned max_n_read,
                               unsigned min_cov_aln, unsigned max_cov_aln);
@@ -199,6 +200,27 @@ int fcx_parser_take(fcx_parser *, uint32_t max_blocks, uint64_t max_bases, const
  * 1..FCX_LANES; with 1 the per-kernel timings of fcx_last_stats are not inflated by overlap),
  * "profile" (0/1). */
 int fcx_set_option(fcx_ctx *, const char *name, double value);
+
+/* ---- several GPUs in one process -------------------------------------------
+ * A fcx_multi owns one engine per listed device.  fcx_multi_pool_upload gives EVERY device the whole
+ * 2-bit read store: device d packs 1/N of the reads from host memory, the other devices receive that
+ * part by a peer copy (NVLink).  fcx_multi_consensus_blocks cuts the seed blocks into N contiguous
+ * cost-balanced slices, runs slice d on device d and returns the results merged in seed order -- the
+ * ordering contract of exe_pool.imap (falcon_kit/mains/consensus.py:274).  Same argument meaning,
+ * ownership and error behaviour as the single-device calls. */
+typedef struct fcx_multi fcx_multi;
+int fcx_multi_create(const int *devices, int n_devices, fcx_multi **out);
+void fcx_multi_destroy(fcx_multi *);
+const char *fcx_multi_last_error(const fcx_multi *);
+int fcx_multi_device_count(const fcx_multi *);
+int fcx_multi_set_option(fcx_multi *, const char *name, double value);
+int fcx_multi_pool_upload(fcx_multi *, const char *bases, const uint64_t *offsets, uint32_t n_reads);
+uint64_t fcx_multi_peer_bytes(const fcx_multi *);   /* bytes moved GPU-to-GPU by the last pool upload */
+int fcx_multi_consensus_blocks(fcx_multi *, uint32_t n_blocks, const uint32_t *block_off,
+                               const uint32_t *read_ids, unsigned min_cov, unsigned K, double min_idt,
+                               const char **out_bases, const uint64_t **out_off);
+int fcx_multi_last_pair_info(fcx_multi *, fcx_pair_info *out, uint64_t max_pairs, uint64_t *n_pairs);
+int fcx_multi_last_stats(fcx_multi *, double *times_ms, uint64_t *counters);
 
 /* CUDA-event stopwatch on the engine's stream: start records an event, stop records a second one,
  * waits for it and returns the elapsed device time in milliseconds. */

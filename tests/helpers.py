@@ -74,3 +74,16 @@ def emu_engine():
             self.n_reads = 0
 
     return EmuEngine()
+
+
+def emu_multi_engine(n_devices=2):
+    """falcon_b200.binding.MultiEngine on the emulator build (FCX_EMU_DEVICES fake devices)."""
+    from falcon_b200 import binding
+    os.environ["FCX_EMU_DEVICES"] = str(n_devices)
+
+    class EmuMulti(binding.MultiEngine):
+        def __init__(self, devices):
+            self._lib = binding.load_library(build_emu())
+            self._open(devices)
+
+    return EmuMulti(list(range(n_devices)))

@@ -120,3 +120,51 @@ def test_waves_and_capacity_retry(oracle):
     assert e1.consensus_blocks(blocks, 4, 0.70) == a
     for bi in (0, 6):
         assert a[bi] == oracle.generate_consensus(S.block_seqs(bi), 4, 0.70)
+
+
+def test_multi_engine_shards_and_merges_in_order(emu, oracle):
+    """fcx_multi_* with 3 (emulated) devices: the read store is assembled from per-device parts,
+    blocks are sharded, the merged output equals the single-engine output block for block."""
+    from helpers import emu_multi_engine
+    S = synth.make_set(40000, 3000, 16, seed=21, n_blocks=8)
+    blocks = [b.tolist() for b in S.blocks]
+    emu.upload_pool(S.pool)
+    single = emu.consensus_blocks(blocks, 3, 0.70)
+    info1 = emu.pair_info()
+    m = emu_multi_engine(3)
+    m.upload_pool(S.pool)
+    assert m.peer_bytes() > 0
+    multi = m.consensus_blocks(blocks, 3, 0.70)
+    assert multi == single
+    info3 = m.pair_info()
+    assert [(i.s1, i.e1, i.dist, i.accepted) for i in info3] == [(i.s1, i.e1, i.dist, i.accepted) for i in info1]
+    assert m.stats()["pairs"] == S.n_pairs
+    assert multi[0] == oracle.generate_consensus(S.block_seqs(0), 3, 0.70)
+    # fewer blocks than devices, and a single block
+    assert m.consensus_blocks(blocks[:2], 3, 0.70) == single[:2]
+    assert m.consensus_blocks(blocks[5:6], 3, 0.70) == single[5:6]
+
+
+def test_cli_streams_and_devices(tmp_path, emu, oracle):
+    """The drop-in command with several producers: two --stream IN:OUT pairs served by one process
+    (parser threads + one GPU loop), each output in its own input order and equal to the
+    single-stream output; and the stdin path equal to the oracle-backed host logic."""
+    import io
+    from falcon_b200 import consensus
+    from helpers import OracleEngine
+    S = synth.make_set(30000, 2500, 14, seed=5, n_blocks=6)
+    texts = [S.la4falcon_text([0, 1, 2]), S.la4falcon_text([3, 4, 5])]
+    want = []
+    for t in texts:
+        out = io.StringIO()
+        a = consensus.parse_args(["consensus", "--output-multi", "--min-cov", "2", "--min-n-read", "1", "--min-cov-aln", "0"])
+        consensus.run(a, stdin=io.BytesIO(t), stdout=out, engine=OracleEngine(oracle))
+        want.append(out.getvalue())
+        assert out.getvalue().count(">") >= 3
+    argv = ["consensus", "--output-multi", "--min-cov", "2", "--min-n-read", "1", "--min-cov-aln", "0", "--batch-blocks", "2"]
+    for i, t in enumerate(texts):
+        (tmp_path / ("in%d" % i)).write_bytes(t)
+        argv += ["--stream", "%s:%s" % (tmp_path / ("in%d" % i), tmp_path / ("out%d" % i))]
+    consensus.run(consensus.parse_args(argv), engine=emu)
+    for i in range(2):
+        assert (tmp_path / ("out%d" % i)).read_text() == want[i]
