@@ -113,6 +113,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
                                          C.POINTER(C.c_void_p)]
     lib.fcx_last_pair_info.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     lib.fcx_last_stats.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+    lib.fcx_align_pairs.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.fcx_multi_create.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]
     lib.fcx_multi_destroy.argtypes = [C.c_void_p]
     lib.fcx_multi_last_error.argtypes = [C.c_void_p]
@@ -290,6 +291,18 @@ class Engine:
         """One seed block given as sequences (seqs[0] = seed), like the reference call."""
         self.upload_pool(seqs)
         return self.consensus_blocks([list(range(len(seqs)))], min_cov, min_idt, K)[0]
+
+    def align_pairs(self, q_ids: Sequence[int], t_ids: Sequence[int], ranges=None, band_tolerance: int = 1500):
+        """Batched DWA.align of pool sequences (graph_to_contig.get_aln_data), distance only.
+        -> int32 array [n, 4]: aln_str_size, dist, aln_q_e, aln_t_e."""
+        q = np.ascontiguousarray(q_ids, dtype=np.uint32)
+        t = np.ascontiguousarray(t_ids, dtype=np.uint32)
+        r = None if ranges is None else np.ascontiguousarray(ranges, dtype=np.int32).reshape(-1, 4)
+        out = np.zeros((q.shape[0], 4), dtype=np.int32)
+        self._check(self._lib.fcx_align_pairs(self._h, q.shape[0], q.ctypes.data, t.ctypes.data,
+                                              None if r is None else r.ctypes.data, band_tolerance, out.ctypes.data),
+                    "fcx_align_pairs")
+        return out
 
     # -- diagnostics --------------------------------------------------------------------
     def pair_info(self) -> List[PairInfo]:

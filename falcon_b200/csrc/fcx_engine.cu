@@ -266,9 +266,10 @@ extern "C" int fcx_pool_reserve(fcx_ctx* ctx, const uint64_t* offsets, uint32_t 
     uint64_t w = 0;
     for (uint32_t r = 0; r < n_reads; r++) {
         uint64_t len = offsets[r + 1] - offsets[r];
-        // the reference truncates reads at 100000 bases (consensus.py:178-179) and asserts
-        // t_len < 100000 for the seed only (falcon.c:343): seeds are checked per block
-        if (len > 100000) { ctx->err = "read longer than 100000 bases (the reference truncates at consensus.py:178-179)"; return 1; }
+        // any length may live in the pool (fcx_align_pairs takes contig-sized sequences); the limits
+        // of the consensus path -- reads <= 100000 (consensus.py:178-179), seeds < 100000
+        // (falcon.c:343) -- are checked per block in fcx_consensus_blocks
+        if (len > 0x7fffff00ull) { ctx->err = "sequence longer than 2^31 bases"; return 1; }
         ctx->h_len[r] = (int32_t)len;
         ctx->h_woff[r] = w;
         uint64_t words = (len + 15) / 16 + 1;            // +1 zero pad word: fetch16 reads one word ahead
@@ -642,6 +643,8 @@ extern "C" int fcx_consensus_blocks(fcx_ctx* ctx, uint32_t n_blocks, const uint3
         if (block_off[b + 1] - block_off[b] > 65000) { ctx->err = "more than 65000 reads in one block"; return 1; }
         for (uint32_t i = block_off[b]; i < block_off[b + 1]; i++)
             if (read_ids[i] >= ctx->n_reads) { ctx->err = "read id outside the uploaded pool"; return 1; }
+        for (uint32_t i = block_off[b]; i < block_off[b + 1]; i++)
+            if (ctx->h_len[read_ids[i]] > 100000) { ctx->err = "read longer than 100000 bases in a seed block (the reference truncates at consensus.py:178-179)"; return 1; }
         if (ctx->h_len[read_ids[block_off[b]]] >= 100000) { ctx->err = "seed of 100000 bases or more (the reference asserts t_len < 100000, falcon.c:343)"; return 1; }
     }
     // ---- plan waves from upper bounds (exact sizes are computed per wave after k_range).
@@ -790,6 +793,47 @@ extern "C" int fcx_timer_stop(fcx_ctx* ctx, double* ms) {
 extern "C" int fcx_internal_want_eqv(fcx_ctx* ctx, int on) { ctx->want_eqv = on != 0; return 0; }
 extern "C" int fcx_internal_last_eqv(fcx_ctx* ctx, const int32_t** eqv, uint64_t* n) {
     *eqv = ctx->out_eqv.data(); *n = ctx->out_eqv.size(); return 0;
+}
+
+// Batched banded alignment of pool sequences (distance only), for stage-2 style callers:
+// falcon_kit/mains/graph_to_contig.py:50-103 calls DWA.align(q[s1:e1], e1-s1, t[s2:e2], e2-s2, 1500, 1)
+// per contig pair and keeps aln_str_size and dist.
+extern "C" int fcx_align_pairs(fcx_ctx* ctx, uint32_t n, const uint32_t* q_ids, const uint32_t* t_ids,
+                               const int32_t* ranges, int band_tolerance, fcx_align_result* out) {
+    CK(cudaSetDevice(ctx->device));
+    if (band_tolerance < 0 || band_tolerance * 2 + 4 > AL_VRING) { ctx->err = "fcx_align_pairs: band_tolerance out of range (<= 4094)"; return 1; }
+    if (n == 0) return 0;
+    std::vector<AlignJob> jobs(n);
+    for (uint32_t i = 0; i < n; i++) {
+        if (q_ids[i] >= ctx->n_reads || t_ids[i] >= ctx->n_reads) { ctx->err = "fcx_align_pairs: sequence id outside the uploaded pool"; return 1; }
+        const int ql = ctx->h_len[q_ids[i]], tl = ctx->h_len[t_ids[i]];
+        int s1 = 0, e1 = ql, s2 = 0, e2 = tl;
+        if (ranges) { s1 = ranges[4 * i]; e1 = ranges[4 * i + 1]; s2 = ranges[4 * i + 2]; e2 = ranges[4 * i + 3]; }
+        if (s1 < 0 || e1 < s1 || e1 > ql || s2 < 0 || e2 < s2 || e2 > tl) { ctx->err = "fcx_align_pairs: range outside its sequence"; return 1; }
+        const long long max_d = (long long)(int)(0.3 * ((e1 - s1) + (e2 - s2)));
+        if ((long long)INT_MAX < max_d * (long long)(band_tolerance * 2 + 1) * 2LL) {   // DW_banded.c:158-161
+            ctx->err = "fcx_align_pairs: lens are too big (the reference aborts here, DW_banded.c:158-161)"; return 1;
+        }
+        jobs[i].q_woff = ctx->h_woff[q_ids[i]]; jobs[i].t_woff = ctx->h_woff[t_ids[i]];
+        jobs[i].qs = s1; jobs[i].q_len = e1 - s1; jobs[i].ts = s2; jobs[i].t_len = e2 - s2;
+    }
+    cudaStream_t st = ctx->stream;
+    CK(ctx->d_trace1.reserve((size_t)n * sizeof(AlignJob)));
+    CK(ctx->d_aln1.reserve((size_t)n * sizeof(PairAln)));
+    CK(cudaMemcpyAsync(ctx->d_trace1.p, jobs.data(), (size_t)n * sizeof(AlignJob), cudaMemcpyHostToDevice, st));
+    FCX_LAUNCH(k_align_batch, std::min<unsigned>(n, (unsigned)ctx->sm_count * 6u), 32, 0, st, ctx->d_pool.as<uint32_t>(),
+               ctx->d_trace1.as<AlignJob>(), n, band_tolerance, ctx->d_aln1.as<PairAln>());
+    CK(cudaGetLastError());
+    std::vector<PairAln> res(n);
+    CK(cudaMemcpyAsync(res.data(), ctx->d_aln1.p, (size_t)n * sizeof(PairAln), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (uint32_t i = 0; i < n; i++) {
+        out[i].aln_str_size = res[i].aligned ? res[i].aln_size : 0;
+        out[i].dist = res[i].aligned ? res[i].dist : 0;
+        out[i].aln_q_e = res[i].aligned ? res[i].q_e : 0;
+        out[i].aln_t_e = res[i].aligned ? res[i].t_e : 0;
+    }
+    return 0;
 }
 
 // single-pair align(): see k_align1 / k_align1_tb

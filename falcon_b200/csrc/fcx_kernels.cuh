@@ -1013,6 +1013,81 @@ k_align1(const uint32_t* __restrict__ pool, uint64_t q_woff, uint64_t t_woff, in
     if (lane == 0) *out = res;
 }
 
+// Batched, distance-only form of the same alignment for stage-2 style callers
+// (falcon_kit/mains/graph_to_contig.py:50-103 keeps only aln_str_size and dist of
+// DWA.align(q[s1:e1], .., t[s2:e2], .., 1500, 1)): one warp per job, no trace.
+struct AlignJob { uint64_t q_woff, t_woff; int32_t qs, q_len, ts, t_len; };
+
+__global__ void __launch_bounds__(32)
+k_align_batch(const uint32_t* __restrict__ pool, const AlignJob* __restrict__ jobs, uint32_t n_jobs, int band_tol,
+              PairAln* __restrict__ out) {
+    __shared__ int V[AL_VRING];
+    const int lane = threadIdx.x;
+    for (uint32_t jb = blockIdx.x; jb < n_jobs; jb += gridDim.x) {
+        const AlignJob J = jobs[jb];
+        const uint32_t* q = pool + J.q_woff; const uint32_t* t = pool + J.t_woff;
+        const int qs = J.qs, ts = J.ts, q_len = J.q_len, t_len = J.t_len;
+        PairAln res; res.aligned = res.dist = res.aln_size = res.q_e = res.t_e = res.k_end = 0;
+        res.accepted = res.t_cnt = res.n_tags = res.cells = 0;
+        const int max_d = (int)(0.3 * (q_len + t_len));
+        const int band_size = band_tol * 2;
+        int best_m = -1, min_k = 0, max_k = 0;
+        bool aligned = false; int end_d = 0, end_k = 0, end_x = 0, end_y = 0;
+        __syncwarp();
+        for (int d = 0; d < max_d; d++) {
+            if (max_k - min_k > band_size) break;
+            const int ncell = ((max_k - min_k) >> 1) + 1;
+            const int nch = (ncell + 31) >> 5;
+            int step_best = best_m;
+            for (int c = 0; c < nch; c++) {
+                const int k = min_k + 2 * (lane + 32 * c);
+                const bool act = k <= max_k;
+                int x = 0, y = 0;
+                if (act) {
+                    if (d > 0) {
+                        const int vm = V[(k - 1) & (AL_VRING - 1)], vp = V[(k + 1) & (AL_VRING - 1)];
+                        const bool up = (k == min_k) || (k != max_k && vm < vp);
+                        x = up ? vp : vm + 1;
+                    }
+                    y = x - k;
+                    snake(q, t, qs, ts, q_len, t_len, x, y);
+                }
+                const unsigned finb = __ballot_sync(FULL, act && (x >= q_len || y >= t_len));
+                if (act) V[k & (AL_VRING - 1)] = x;
+                step_best = max(step_best, __reduce_max_sync(FULL, act ? x + y : INT_MIN));
+                if (finb) {
+                    const int fl = __ffs(finb) - 1;
+                    aligned = true; end_d = d; end_k = min_k + 2 * (fl + 32 * c);
+                    end_x = __shfl_sync(FULL, x, fl); end_y = __shfl_sync(FULL, y, fl);
+                    break;
+                }
+            }
+            if (aligned) break;
+            best_m = step_best;
+            __syncwarp();
+            int nmin = INT_MAX, nmax = INT_MIN;
+            const int thr = best_m - band_tol;
+            for (int c = 0; c < nch; c++) {
+                const int k = min_k + 2 * (lane + 32 * c);
+                bool ok = false;
+                if (k <= max_k) { const int x = V[k & (AL_VRING - 1)]; ok = (2 * x - k) >= thr; }
+                const unsigned okb = __ballot_sync(FULL, ok);
+                if (okb) {
+                    if (nmin == INT_MAX) nmin = min_k + 2 * (__ffs(okb) - 1 + 32 * c);
+                    nmax = min_k + 2 * (31 - __clz(okb) + 32 * c);
+                }
+            }
+            max_k = nmax + 1; min_k = nmin - 1;
+            __syncwarp();
+        }
+        if (aligned) {
+            res.aligned = 1; res.dist = end_d; res.q_e = end_x; res.t_e = end_y; res.k_end = end_k;
+            res.aln_size = (end_x + end_y + end_d) / 2;
+        }
+        if (lane == 0) out[jb] = res;
+    }
+}
+
 __global__ void k_align1_tb(const uint32_t* __restrict__ pool, uint64_t q_woff, uint64_t t_woff, int q_len, int t_len,
                             const uint32_t* __restrict__ trace, int rec_words, uint32_t* __restrict__ path,
                             const PairAln* __restrict__ alnp, char* __restrict__ q_aln, char* __restrict__ t_aln) {

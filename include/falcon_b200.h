@@ -201,6 +201,15 @@ int fcx_parser_take(fcx_parser *, uint32_t max_blocks, uint64_t max_bases, const
  * "profile" (0/1). */
 int fcx_set_option(fcx_ctx *, const char *name, double value);
 
+/* Batched banded alignment of sequences of the uploaded pool, distance only: the per-pair call of
+ * falcon_kit/mains/graph_to_contig.py:50-103 -- DWA.align(q[s1:e1], e1-s1, t[s2:e2], e2-s2, 1500, 1),
+ * of which the caller keeps aln_str_size and dist -- for n pairs at once, one warp per pair.
+ * ranges: 4 ints (s1, e1, s2, e2) per pair, or NULL for whole sequences.  Results are those of the
+ * reference's align() (src/c/DW_banded.c:115-330): aln_str_size 0 means "not aligned". */
+typedef struct { int32_t aln_str_size, dist, aln_q_e, aln_t_e; } fcx_align_result;
+int fcx_align_pairs(fcx_ctx *, uint32_t n_pairs, const uint32_t *q_ids, const uint32_t *t_ids,
+                    const int32_t *ranges, int band_tolerance, fcx_align_result *out);
+
 /* ---- several GPUs in one process -------------------------------------------
  * A fcx_multi owns one engine per listed device.  fcx_multi_pool_upload gives EVERY device the whole
  * 2-bit read store: device d packs 1/N of the reads from host memory, the other devices receive that

@@ -168,3 +168,29 @@ def test_cli_streams_and_devices(tmp_path, emu, oracle):
     consensus.run(consensus.parse_args(argv), engine=emu)
     for i in range(2):
         assert (tmp_path / ("out%d" % i)).read_text() == want[i]
+
+
+def test_batched_align_pairs(emu, oracle):
+    """fcx_align_pairs: the graph_to_contig-style call (band 1500, sub-ranges, sequences longer than
+    the 100000-base limit of the consensus path) against the oracle's align()."""
+    rng = np.random.default_rng(3)
+    g = synth.random_codes(120000, rng)
+    a = synth.codes_to_bytes(synth.add_errors(g[:9000], rng, 0.02, 0.01, 0.01))
+    b = synth.codes_to_bytes(synth.add_errors(g[200:9500], rng, 0.02, 0.01, 0.01))
+    big_a = synth.codes_to_bytes(synth.add_errors(g, rng, 0.005, 0.003, 0.002))      # > 100000 bases
+    big_b = synth.codes_to_bytes(synth.add_errors(g, rng, 0.005, 0.003, 0.002))
+    unrelated = synth.codes_to_bytes(synth.random_codes(4000, rng))
+    pool = [a, b, big_a, big_b, unrelated]
+    emu.upload_pool(pool)
+    jobs = [(0, 1, (250, 8000, 40, 7900), 1500), (0, 1, (250, 8000, 40, 7900), 150), (0, 4, None, 1500),
+            (2, 3, (100000, 110000, 100000, 110050), 1500)]
+    for qi, ti, rg, band in jobs:
+        got = emu.align_pairs([qi], [ti], None if rg is None else [rg], band)[0]
+        q = pool[qi] if rg is None else pool[qi][rg[0]:rg[1]]
+        t = pool[ti] if rg is None else pool[ti][rg[2]:rg[3]]
+        o = oracle.align(q, t, band)
+        assert got[0] == o["aln_str_size"]
+        if o["aln_str_size"] > 0:
+            assert (got[1], got[2], got[3]) == (o["dist"], o["q_e"], o["t_e"])
+    many = emu.align_pairs([0, 0, 1], [1, 1, 0], None, 1500)
+    assert (many[0] == many[1]).all() and many[0][0] > 0
