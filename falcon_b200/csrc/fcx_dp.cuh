@@ -58,7 +58,7 @@ __device__ __forceinline__ int dp3_snake16(const uint32_t* __restrict__ q, const
 __global__ void __launch_bounds__(DP3_WARPS * 32)
 k_dp3(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs,
       const PairRange* __restrict__ ranges, const PairAlloc* __restrict__ allocs, uint32_t n_pairs,
-      const uint32_t* __restrict__ pool, uint32_t* __restrict__ trace_arena, double max_diff,
+      const uint32_t* __restrict__ pool, uint32_t* trace_arena, uint32_t* __restrict__ path_arena, double max_diff,
       uint32_t* __restrict__ next_pair, PairAln* __restrict__ out) {
     __shared__ int s_V[DP3_WARPS][VRING];          // wide mode only
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -291,7 +291,9 @@ k_dp3(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs,
     }
     res.cells = cells;
     if (lane == 0) out[p] = res;
-    __syncwarp();                       // wide mode: the ring is reused by the next pair
+    __syncwarp();                       // wide mode: the ring is reused by the next pair; lane 0's trace records are visible
+    // the backward walk of an accepted pair, while its last records are still in L2
+    if (res.accepted == 1) warp_walk_back(trace, path_arena + al.path_off, end_d, end_k, lane);
   }
 }
 

@@ -449,10 +449,10 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
     CKL(cudaStreamSynchronize(st));
     // ---- exact per-pair allocations
     std::vector<PairAlloc> ha(np);
-    uint64_t trace_recs = 0, xam_n = 0, path_w = 0, dp_pairs = 0, span_bases = 0; uint32_t max_span = 0;
+    uint64_t trace_recs = 0, xam_n = 0, xck_n = 0, path_w = 0, dp_pairs = 0, span_bases = 0; uint32_t max_span = 0;
     const PairRange* hr = L.h_ranges.as<PairRange>();
     for (uint32_t p = 0; p < np; p++) {
-        ha[p].trace_off = trace_recs; ha[p].xam_off = xam_n; ha[p].path_off = path_w; ha[p].trace_cap = 0; ha[p].pad_ = 0;
+        ha[p].trace_off = trace_recs; ha[p].xam_off = xam_n; ha[p].path_off = path_w; ha[p].trace_cap = 0; ha[p].xck_off = (uint32_t)xck_n;
         if (hr[p].pass) {
             int ql = hr[p].e1 - hr[p].s1, tl = hr[p].e2 - hr[p].s2;
             // Only accepted pairs are traced back, and acceptance needs D / A < max_diff with
@@ -461,14 +461,15 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
             const double mdiff = std::max(0.0, 1.0 - min_idt);
             uint64_t md = max_d_of(ql, tl);
             if (mdiff < 1.999) md = std::min<uint64_t>(md, (uint64_t)(mdiff * (ql + tl) / (2.0 - mdiff)) + 2);
-            ha[p].trace_cap = (uint32_t)(md + 1); ha[p].pad_ = 0;
-            trace_recs += md + 1; xam_n += (uint64_t)tl + 2; path_w += md / 32 + 2;
+            ha[p].trace_cap = (uint32_t)(md + 1);
+            trace_recs += md + 1; xam_n += ((uint64_t)tl + 4 + 3) & ~(uint64_t)3; xck_n += (uint64_t)tl / 32 + 2; path_w += md / 32 + 2;
             dp_pairs++; span_bases += (uint64_t)ql + tl;
             max_span = std::max(max_span, (uint32_t)std::max(ql, tl));
         }
     }
     CKR(L.d_trace.reserve(trace_recs * TRACE_REC_WORDS * 4 + 64));
-    CKR(L.d_xam.reserve(xam_n * 4 + 128));
+    if (xck_n > 0xffffffffull) { L.err = "out of device memory (checkpoint index)"; return 100; }    // split the wave
+    CKR(L.d_xam.reserve(xck_n * 4 + 128));
     CKR(L.d_ent.reserve(xam_n * 4 + 128));
     CKR(L.d_path.reserve(path_w * 4 + 64));
     if (np) CKL(cudaMemcpyAsync(L.d_allocs.p, ha.data(), (size_t)np * sizeof(PairAlloc), cudaMemcpyHostToDevice, st));
@@ -482,7 +483,7 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
             const unsigned dp_grid = std::min<unsigned>((np + DP3_WARPS - 1) / DP3_WARPS, (unsigned)ctx->sm_count * 32u);
             FCX_LAUNCH(k_dp3, dp_grid, DP3_WARPS * 32, 0, st,
                        L.d_blocks.as<BlockDesc>(), L.d_pairs.as<PairDesc>(), L.d_ranges.as<PairRange>(),
-                       L.d_allocs.as<PairAlloc>(), np, pool, L.d_trace.as<uint32_t>(), 1.0 - min_idt,
+                       L.d_allocs.as<PairAlloc>(), np, pool, L.d_trace.as<uint32_t>(), L.d_path.as<uint32_t>(), 1.0 - min_idt,
                        L.d_counter.as<uint32_t>(), L.d_aln.as<PairAln>());
         } else {
             // round-1 kernels kept for A/B measurement: shared-memory V ring, lanes re-mapped to the
@@ -511,11 +512,6 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
     CKL(cudaEventRecord(L.ev[4], st));
     // ---- traceback
     if (np) {
-        const uint64_t n16 = (xam_n + 3) / 4 + 1;
-        FCX_LAUNCH(k_fill32, (unsigned)std::min<uint64_t>((n16 + 255) / 256, (uint64_t)ctx->sm_count * 16), 256, 0, st,
-            L.d_ent.as<uint4>(), n16, ENT_PLAIN);
-        CKL(cudaGetLastError());
-        L.counters[FCX_C_KERNEL_LAUNCHES] += 1;
         CKL(cudaMemsetAsync(L.d_vmeta.p, 0, (size_t)np * sizeof(VoteMeta), st));
         // accepted pairs ordered by dist (longest first): warps of k_traceback walk paths of similar length
         CKR(L.d_tbhist.reserve((TB_BUCKETS + 8) * 4));
@@ -526,10 +522,17 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
         FCX_LAUNCH(k_tb_scatter, (np + 255) / 256, 256, 0, st, L.d_aln.as<PairAln>(), np, L.d_tbhist.as<uint32_t>(),
                    L.d_order.as<uint32_t>());
         CKL(cudaGetLastError());
+        if (ctx->dp_variant != 3) {       // k_dp3 walks back inside the DP warp
+            FCX_LAUNCH(k_traceback_walk, (unsigned)std::min<uint32_t>((np + 3) / 4, (uint32_t)ctx->sm_count * 16u), 128, 0, st,
+                L.d_allocs.as<PairAlloc>(), L.d_order.as<uint32_t>(), L.d_tbhist.as<uint32_t>() + TB_BUCKETS,
+                L.d_trace.as<uint32_t>(), L.d_path.as<uint32_t>(), L.d_aln.as<PairAln>());
+            CKL(cudaGetLastError());
+            L.counters[FCX_C_KERNEL_LAUNCHES] += 1;
+        }
         FCX_LAUNCH(k_traceback, (np + 127) / 128, 128, 0, st,
             L.d_blocks.as<BlockDesc>(), L.d_pairs.as<PairDesc>(), L.d_ranges.as<PairRange>(),
             L.d_allocs.as<PairAlloc>(), L.d_order.as<uint32_t>(), L.d_tbhist.as<uint32_t>() + TB_BUCKETS, pool,
-            L.d_trace.as<uint32_t>(), L.d_path.as<uint32_t>(),
+            L.d_path.as<uint32_t>(),
             L.d_xam.as<uint32_t>(), L.d_ent.as<uint32_t>(), L.d_vmeta.as<VoteMeta>(), L.d_aln.as<PairAln>());
         CKL(cudaGetLastError());
         L.counters[FCX_C_KERNEL_LAUNCHES] += 4;
@@ -551,7 +554,7 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
     CKL(cudaEventRecord(L.ev[7], st));
     cudaStream_t sh = L.stream_hi;
     CKL(cudaStreamWaitEvent(sh, L.ev[7], 0));
-    FCX_LAUNCH(k_cns_dp, (nb + CDP_THREADS - 1) / CDP_THREADS, CDP_THREADS, 0, sh,
+    FCX_LAUNCH(k_cns_dp, (nb + CDP_WARPS - 1) / CDP_WARPS, CDP_WARPS * 32, 0, sh,
         L.d_blocks.as<BlockDesc>(), nb, L.d_vmeta.as<VoteMeta>(), L.d_slots.as<uint2>(), L.d_ovf.as<uint2>(),
         L.d_recs.as<CnsRec>(), L.d_lvl.as<int32_t>(), L.d_cns.as<char>(), L.d_eqv.as<int32_t>(),
         ctx->want_eqv ? 1 : 0, min_cov, L.d_cnsout.as<CnsOut>());

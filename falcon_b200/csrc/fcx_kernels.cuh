@@ -69,10 +69,11 @@ struct PairRange {        // output of k_range
 
 struct PairAlloc {        // host-computed after k_range
     uint64_t trace_off;   // in 32-byte trace records
-    uint64_t xam_off;     // in uint32 entries
+    uint64_t xam_off;     // in uint32 entries (a multiple of 4): the pair's ent[] array
     uint64_t path_off;    // in uint32 words
     uint32_t trace_cap;   // trace records available: steps d >= trace_cap are not recorded (such a
-    uint32_t pad_;        // pair can no longer be accepted, see fcx_engine.cu)
+                          // pair can no longer be accepted, see fcx_engine.cu)
+    uint32_t xck_off;     // in uint32 entries: query-index checkpoints, one per 32 target columns
 };
 
 struct PairAln {          // output of k_dp / k_traceback
@@ -84,7 +85,7 @@ struct PairAln {          // output of k_dp / k_traceback
 };
 
 // per pair, written by k_traceback for accepted pairs (all-zero = not accepted): what k_vote needs
-struct VoteMeta { uint64_t ent_off; uint64_t q_woff; int32_t t_start, t_cnt, q_s, pad; };
+struct VoteMeta { uint64_t ent_off; uint64_t q_woff; int32_t t_start, t_cnt, q_s; uint32_t xck_off; };
 
 // ------------------------------------------------------------------------------ helpers
 __device__ __forceinline__ uint32_t fetch16(const uint32_t* __restrict__ w, int pos) {
@@ -737,6 +738,9 @@ k_dp(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs,
     if (lane == 0) out[p] = res;
 }
 
+__device__ __forceinline__ void warp_walk_back(const uint32_t* trace, uint32_t* __restrict__ path,
+                                               const int D, int k, const int lane);
+
 }  // namespace fcx
 
 #include "fcx_dp.cuh"
@@ -744,11 +748,9 @@ k_dp(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs,
 namespace fcx {
 
 // ------------------------------------------------------------------------------ k_traceback
-// One thread per accepted pair.  (1) walk the trace records backwards collecting the direction
-// bit of every step of the optimal path (DW_banded.c:264-277); (2) replay the path forwards,
-// recomputing the snakes, and emit per target position y two records:
-//        xam[y] = (x << 1) | is_match      x = query index when target base y is consumed
-//                                          (sentinel xam[t_cnt] = x_end << 1)
+// (1) warp_walk_back: walk the trace records backwards collecting the direction bit of every step
+// of the optimal path (DW_banded.c:264-277); (2) k_traceback, one thread per accepted pair: replay
+// the path forwards, recomputing the snakes, and emit per target position y
 //        ent[y] = VALID | is_match<<30 | n_ins<<22 | first 11 inserted bases (2 bits each)
 // This is get_align_tags (falcon.c:106-162) in closed form: the delta-0 tag of column y carries
 // the seed base (match) or '-', and the insertion tags delta = 1..n_ins are the query bases
@@ -799,13 +801,63 @@ __global__ void k_tb_scatter(const PairAln* __restrict__ aln, uint32_t n_pairs, 
     if (a.accepted > 0) order[atomicAdd(&cursor[tb_bucket(a.dist)], 1u)] = p;
 }
 
+// Backward walk of one pair by a whole warp (DW_banded.c:264-277): bit d of path[] = "step d came
+// from k+1" (a target-only column).  Lane l holds the record of step 32w + l, so one coalesced
+// request brings 32 records (1 KB); the 32 dependent steps then run on shuffles.  Called by the DP
+// warp right after the forward pass of an accepted pair (k_dp3), or by k_traceback_walk for the
+// round-1 DP kernels.
+__device__ __forceinline__ void warp_walk_back(const uint32_t* trace, uint32_t* __restrict__ path,
+                                               const int D, int k, const int lane) {
+    for (int w = D >> 5; w >= 0; w--) {
+        const int d_l = 32 * w + lane;
+        uint32_t mk = 0, w0 = 0, w1 = 0;
+        if (d_l >= 1 && d_l <= D) {
+            const uint32_t* rec = trace + (size_t)d_l * TRACE_REC_WORDS;
+            const uint2 hd = *reinterpret_cast<const uint2*>(rec);
+            mk = hd.x; w0 = hd.y; w1 = rec[2];
+        }
+        uint32_t acc = 0;
+        const int l_hi = min(31, D - 32 * w), l_lo = w == 0 ? 1 : 0;
+        for (int l = l_hi; l >= l_lo; l--) {
+            const int idx = (k - (int)__shfl_sync(FULL, mk, l)) >> 1;
+            uint32_t word = __shfl_sync(FULL, idx < 32 ? w0 : w1, l);
+            if (idx >= 64) word = trace[(size_t)(32 * w + l) * TRACE_REC_WORDS + 1 + (idx >> 5)];   // wide bands: rare
+            const uint32_t up = (word >> (idx & 31)) & 1u;
+            acc |= up << l;
+            k += up ? 1 : -1;
+        }
+        if (lane == 0) path[w] = acc;
+    }
+}
+
+// the same walk for pairs whose forward pass was done by k_dp<> (dp_variant 1 / 2): one warp per
+// accepted pair
+__global__ void __launch_bounds__(128)
+k_traceback_walk(const PairAlloc* __restrict__ allocs, const uint32_t* __restrict__ order,
+                 const uint32_t* __restrict__ n_order, const uint32_t* trace_arena,
+                 uint32_t* __restrict__ path_arena, const PairAln* __restrict__ aln) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t n = *n_order;
+    for (uint32_t slot = blockIdx.x * 4 + (threadIdx.x >> 5); slot < n; slot += gridDim.x * 4) {
+        const uint32_t p = order[slot];
+        const PairAlloc al = allocs[p];
+        const PairAln a = aln[p];
+        warp_walk_back(trace_arena + al.trace_off * TRACE_REC_WORDS, path_arena + al.path_off, a.dist, a.k_end, lane);
+    }
+}
+
+// One thread per accepted pair: forward replay of the path.  Every target column y gets its entry
+// ent[y]; entries are produced in ascending y, collected four at a time in registers and stored as
+// one 16-byte vector, so that the array is written densely and exactly once (no pre-fill, no
+// partial-sector read-modify-write).  xck[y >> 5] = query index at column y for every 32nd column:
+// k_vote needs the query index only to fetch inserted bases beyond the 11 inline ones (xck_lookup).
 __global__ void __launch_bounds__(128)
 k_traceback(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs,
             const PairRange* __restrict__ ranges, const PairAlloc* __restrict__ allocs,
             const uint32_t* __restrict__ order, const uint32_t* __restrict__ n_order,
             const uint32_t* __restrict__ pool,
-            const uint32_t* __restrict__ trace_arena, uint32_t* __restrict__ path_arena,
-            uint32_t* __restrict__ xam_arena, uint32_t* __restrict__ ent_arena,
+            const uint32_t* __restrict__ path_arena,
+            uint32_t* __restrict__ xck_arena, uint32_t* __restrict__ ent_arena,
             VoteMeta* __restrict__ vmeta, PairAln* __restrict__ aln) {
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= *n_order) return;
@@ -817,46 +869,13 @@ k_traceback(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ p
     const uint32_t* t = pool + blocks[pd.block].seed_woff;
     const int qs = rg.s1, ts = rg.s2, q_len = rg.e1 - rg.s1, t_len = rg.e2 - rg.s2;
     const PairAlloc al = allocs[p];
-    const uint32_t* trace = trace_arena + al.trace_off * TRACE_REC_WORDS;
-    uint32_t* path = path_arena + al.path_off;
-    uint32_t* xam = xam_arena + al.xam_off;
-    uint32_t* ent = ent_arena + al.xam_off;
+    const uint32_t* path = path_arena + al.path_off;
+    uint32_t* xck = xck_arena + al.xck_off;
+    uint32_t* ent = ent_arena + al.xam_off;           // 16-byte aligned (xam_off is a multiple of 4)
     const int D = a.dist;
-    // (1) backwards: bit d of path = step d came from k+1 (a target-only column)
-    int k = a.k_end;
-    uint32_t acc = 0;
-    // the record addresses do not depend on the path (only the bit inside does), so the headers
-    // are fetched four steps ahead to overlap the DRAM latency of this pointer chase
-    auto step_back = [&](const int d, const uint2 hd) {
-        const uint32_t* rec = trace + (size_t)d * TRACE_REC_WORDS;
-        const int idx = (k - (int)hd.x) >> 1;
-        const uint32_t w = idx < 32 ? hd.y : __ldg(rec + 1 + (idx >> 5));
-        const uint32_t up = (w >> (idx & 31)) & 1u;
-        acc |= up << (d & 31);
-        if ((d & 31) == 0 || d == 1) { path[d >> 5] = acc; acc = 0; }
-        k += up ? 1 : -1;
-    };
-    int d = D;
-    for (; d >= 4; d -= 4) {
-        const uint2 h0 = __ldg(reinterpret_cast<const uint2*>(trace + (size_t)d * TRACE_REC_WORDS));
-        const uint2 h1 = __ldg(reinterpret_cast<const uint2*>(trace + (size_t)(d - 1) * TRACE_REC_WORDS));
-        const uint2 h2 = __ldg(reinterpret_cast<const uint2*>(trace + (size_t)(d - 2) * TRACE_REC_WORDS));
-        const uint2 h3 = __ldg(reinterpret_cast<const uint2*>(trace + (size_t)(d - 3) * TRACE_REC_WORDS));
-        step_back(d, h0); step_back(d - 1, h1); step_back(d - 2, h2); step_back(d - 3, h3);
-    }
-    for (; d >= 1; d--) step_back(d, __ldg(reinterpret_cast<const uint2*>(trace + (size_t)d * TRACE_REC_WORDS)));
-    // (2) forwards.  ent[] was pre-filled with ENT_PLAIN (= a match column without insertions), so
-    // only the other columns are written: target-only columns and columns followed by query-only
-    // columns.  xam[] (query index at the column, used by the consensus vote to fetch inserted
-    // bases beyond the 11 inline ones) is written at exactly those columns and at y = 0;
-    // xam_lookup() reconstructs it anywhere else.
-    // The loop body is one straight-line "step": the indel of step d, then ONE 16-base compare
-    // (longer snakes are rare and finish in a small loop), all state updates by selects, so that
-    // the 32 pairs of a warp (ordered by dist) stay converged.
     int x = 0, y = 0, run = 0, t_cnt = -1, n_match_cols = 0;
-    uint32_t pend = 0; int pend_y = -1, pend_x = 0;   // entry of the last target column, still open
+    uint32_t pend = 0; int pend_x = 0; bool open = false;     // entry of the last target column, still open
     uint32_t pw = 0;
-    xam[0] = 1u;                                      // column 0 is always a match at x = 0
     // x and y creep forward a few bases per step: keep the current two packed words of each
     // sequence in registers and reload only when the position crosses a word boundary
     int wq_i = -2, wt_i = -2; uint32_t wq_lo = 0, wq_hi = 0, wt_lo = 0, wt_hi = 0;
@@ -870,21 +889,25 @@ k_traceback(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ p
         if (wi != wt_i) { wt_i = wi; wt_lo = __ldg(t + wi); wt_hi = __ldg(t + wi + 1); }
         return __funnelshift_r(wt_lo, wt_hi, (pos & 15) << 1);
     };
-    auto flush = [&]() {          // store the open entry unless it is a plain match column
-        if (pend_y >= 0 && (run > 0 || !(pend & ENT_MATCH))) {
-            ent[pend_y] = pend | ((uint32_t)run << 22);
-            xam[pend_y] = ((uint32_t)pend_x << 1) | ((pend & ENT_MATCH) ? 1u : 0u);
-        }
+    // output cursor: yo = number of entries emitted so far (entry yo goes to ent[yo])
+    int yo = 0; uint32_t b0 = 0, b1 = 0, b2 = 0;
+    auto emit = [&](const uint32_t e, const int xcol) {
+        if ((yo & 31) == 0) xck[yo >> 5] = (uint32_t)xcol;
+        const int r = yo & 3;
+        if (r == 3) *reinterpret_cast<uint4*>(ent + (yo - 3)) = make_uint4(b0, b1, b2, e);
+        b0 = r == 0 ? e : b0; b1 = r == 1 ? e : b1; b2 = r == 2 ? e : b2;
+        yo++;
     };
+    auto close_pending = [&]() { if (open) emit(pend | ((uint32_t)run << 22), pend_x); };
     for (int d = 0; d <= D; d++) {
         if (d > 0) {
             if ((d & 31) == 0 || d == 1) pw = path[d >> 5];
             const bool del = ((pw >> (d & 31)) & 1u) != 0;          // target-only column
             const uint32_t qb = win_q(qs + x) & 3u;                  // the query base of a query-only column
-            if (del) flush();
+            if (del) close_pending();
             const uint32_t ins_bits = run < ENT_INS_INLINE ? qb << (2 * run) : 0u;
             pend = del ? ENT_VALID : (pend | ins_bits);
-            pend_y = del ? y : pend_y; pend_x = del ? x : pend_x;
+            pend_x = del ? x : pend_x; open = true;
             run = del ? 0 : run + 1;
             y += del ? 1 : 0; x += del ? 0 : 1;
             if (run == 255) {            // the 255th consecutive query-only column: tags stop before it
@@ -893,7 +916,7 @@ k_traceback(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ p
                 break;
             }
         }
-        // snake: no per-base stores, interior match columns stay ENT_PLAIN
+        // snake: interior match columns are plain entries
         int rem = min(q_len - x, t_len - y);
         uint32_t diff = win_q(qs + x) ^ win_t(ts + y);
         int adv = min((int)((unsigned)(__ffs(diff) - 1) >> 1), max(min(rem, 16), 0));
@@ -904,29 +927,40 @@ k_traceback(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ p
             if (nn < 16) break;
         }
         if (adv > 0) {
-            flush();
+            close_pending();
+            int left = adv - 1, xc = x;                              // the last match column stays open
+            while (left > 0) {
+                if ((yo & 3) == 0 && left >= 4) {
+                    if ((yo & 31) == 0) xck[yo >> 5] = (uint32_t)xc;
+                    *reinterpret_cast<uint4*>(ent + yo) = make_uint4(ENT_PLAIN, ENT_PLAIN, ENT_PLAIN, ENT_PLAIN);
+                    yo += 4; xc += 4; left -= 4;
+                } else { emit(ENT_PLAIN, xc); xc++; left--; }
+            }
             x += adv; y += adv; n_match_cols += adv;
-            pend = ENT_PLAIN; pend_y = y - 1; pend_x = x - 1; run = 0;
+            pend = ENT_PLAIN; pend_x = x - 1; run = 0; open = true;
         }
     }
-    flush();
+    close_pending();
+    {   // the entries of the last, incomplete vector
+        const int r = yo & 3, base = yo - r;
+        if (r > 0) ent[base] = b0;
+        if (r > 1) ent[base + 1] = b1;
+        if (r > 2) ent[base + 2] = b2;
+    }
     if (t_cnt < 0) t_cnt = y;
     a.t_cnt = t_cnt;
     a.n_tags = t_cnt + (x - n_match_cols);            // target columns + query-only columns among them
     aln[p] = a;
-    VoteMeta vm; vm.ent_off = al.xam_off; vm.q_woff = pd.read_woff; vm.t_start = rg.s2; vm.t_cnt = t_cnt; vm.q_s = rg.s1; vm.pad = 0;
+    VoteMeta vm; vm.ent_off = al.xam_off; vm.q_woff = pd.read_woff; vm.t_start = rg.s2; vm.t_cnt = t_cnt; vm.q_s = rg.s1; vm.xck_off = al.xck_off;
     vmeta[p] = vm;                                    // (zero = "not accepted" for every other pair)
 }
 
-// query index x at target column y of one read: nearest explicitly recorded column at or before y
-// (every non-plain column and column 0 carry xam), then one base per plain match column.
-__device__ __forceinline__ int xam_lookup(const uint32_t* __restrict__ xam, const uint32_t* __restrict__ ent, int y) {
-    int j = y;
-    while (j > 0 && ent[j] == ENT_PLAIN) j--;
-    const int xj = (int)(xam[j] >> 1);
-    if (j == y) return xj;
-    const uint32_t e = ent[j];
-    return xj + ((e & ENT_MATCH) ? 1 : 0) + ent_nins(e) + (y - j - 1);
+// query index x at target column y of one read: the checkpoint of the enclosing 32-column group,
+// then one base per match column and per inserted base of the columns in between
+__device__ __forceinline__ int xck_lookup(const uint32_t* __restrict__ xck, const uint32_t* __restrict__ ent, int y) {
+    int x = (int)xck[y >> 5];
+    for (int j = y & ~31; j < y; j++) { const uint32_t e = ent[j]; x += ((e & ENT_MATCH) ? 1 : 0) + ent_nins(e); }
+    return x;
 }
 
 // ------------------------------------------------------------------------------ k_fill32

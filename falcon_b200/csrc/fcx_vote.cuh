@@ -46,7 +46,7 @@ __device__ __forceinline__ uint32_t lk_key(int delta, int base, uint32_t pred) {
 __global__ void __launch_bounds__(VOTE_TP)
 k_vote(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, uint32_t n_tiles,
        const VoteMeta* __restrict__ vmeta, const uint32_t* __restrict__ pool,
-       const uint32_t* __restrict__ xam_arena, const uint32_t* __restrict__ ent_arena,
+       const uint32_t* __restrict__ xck_arena, const uint32_t* __restrict__ ent_arena,
        uint2* __restrict__ slot_arena, uint2* __restrict__ ovf_arena, uint32_t ovf_cap,
        uint32_t* __restrict__ ovf_next, int* __restrict__ err_flag) {
     const uint32_t T = blockIdx.x;
@@ -102,13 +102,13 @@ k_vote(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, uint32_t n_tiles
             int pb;
             if (pn == 0) pb = (ep & ENT_MATCH) ? Sp : 4;
             else if (pn <= ENT_INS_INLINE) pb = ent_ins(ep, pn - 1);
-            else { x = xam_lookup(xam_arena + vm.ent_off, ent, y); pb = base_at(qr, vm.q_s + x - 1); }
+            else { x = xck_lookup(xck_arena + vm.xck_off, ent, y); pb = base_at(qr, vm.q_s + x - 1); }
             pred = ((uint32_t)pn << 3) | (uint32_t)pb;
         }
         vote(lk_key(0, b0, pred));
         if (nins > 0) {
             maxd = max(maxd, nins);
-            if (nins > ENT_INS_INLINE && x < 0) x = xam_lookup(xam_arena + vm.ent_off, ent, y);
+            if (nins > ENT_INS_INLINE && x < 0) x = xck_lookup(xck_arena + vm.xck_off, ent, y);
             int pb = b0;
             for (int lev = 1; lev <= nins; lev++) {
                 const int bb = lev <= ENT_INS_INLINE ? ent_ins(ec, lev - 1) : base_at(qr, vm.q_s + x + m + lev - 1);
@@ -140,17 +140,35 @@ k_vote(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, uint32_t n_tiles
 }
 
 // ------------------------------------------------------------------------------ k_cns_dp
-constexpr int CDP_THREADS = 32;
+// One WARP per seed block, lanes parallel over the LINKS of the current position.  The chain over
+// positions is inherent (falcon.c:405-475), so what matters is the latency of one link of the chain:
+//   * the position slots do not depend on the chain: they are streamed three loads (six positions)
+//     ahead through registers, 256 coalesced bytes = two positions per load;
+//   * the column scores / record ids of the previous and the current position sit in shared memory
+//     (delta levels < CDP_SL; deeper levels, which need an insertion run of >= CDP_SL bases, fall
+//     back to a per-block global table);
+//   * lane e scores link e; the best link of each of the (<= 5) columns of a delta level is a
+//     warp max-reduction, ties resolved towards the lowest lane = first appearance (the slot keeps
+//     links in first-appearance order inside a level);
+//   * the backtrack walks the record list through a shared-memory window (records are appended in
+//     position order, so the predecessor is almost always a few records back).
+constexpr int CDP_WARPS = 4;
+constexpr int CDP_SL = 12;               // delta levels with shared-memory column tables
 constexpr int CDP_LEVELS = 256;          // deltas 0..255 (the tag cut at 255 keeps delta <= 254)
+constexpr int CDP_WIN = 256;             // records per backtrack window
 
-__global__ void __launch_bounds__(CDP_THREADS)
+__global__ void __launch_bounds__(CDP_WARPS * 32)
 k_cns_dp(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, const VoteMeta* __restrict__ vmeta,
          const uint2* __restrict__ slot_arena, const uint2* __restrict__ ovf_arena,
          CnsRec* __restrict__ rec_arena, int32_t* __restrict__ lvl_scratch,
          char* __restrict__ cns_arena, int32_t* __restrict__ eqv_arena, int want_eqv, unsigned min_cov,
          CnsOut* __restrict__ out) {
-    const uint32_t b = blockIdx.x * CDP_THREADS + threadIdx.x;
-    if (b >= n_blocks) return;
+    __shared__ int32_t s_sc[CDP_WARPS][2][CDP_SL * 5];
+    __shared__ int32_t s_rc[CDP_WARPS][2][CDP_SL * 5];
+    __shared__ int32_t s_win[CDP_WARPS][CDP_WIN * 3];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t b = blockIdx.x * CDP_WARPS + wib;
+    if (b >= n_blocks) return;                    // (no CTA-wide barrier below)
     const BlockDesc bd = blocks[b];
     const int t_len = bd.slen;
     CnsRec* recs = rec_arena + bd.rec_off;
@@ -160,65 +178,59 @@ k_cns_dp(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, const VoteMeta
 
     // first / last target position carrying tags, and whether anything was accepted (falcon.c:651-656)
     int i_lo = INT_MAX, i_hi = 0, R = 0;
-    for (uint32_t j = 0; j < bd.n_pairs; j++) {
+    for (uint32_t j = lane; j < bd.n_pairs; j += 32) {
         const VoteMeta vm = vmeta[bd.pair_begin + j];
         if (vm.t_cnt == 0) continue;
         R++; i_lo = min(i_lo, vm.t_start); i_hi = max(i_hi, vm.t_start + vm.t_cnt);
     }
-    if (R == 0) { cns[0] = 0; out[b] = co; return; }
+    R = __reduce_add_sync(FULL, R); i_lo = __reduce_min_sync(FULL, i_lo); i_hi = __reduce_max_sync(FULL, i_hi);
+    if (R == 0) { if (lane == 0) { cns[0] = 0; out[b] = co; } return; }
     i_hi = min(i_hi, t_len);
     co.positions = i_hi - i_lo;
 
     // column scores / record ids of the previous and the current position, indexed delta * 5 + base
-    int32_t* tab = lvl_scratch + (size_t)b * (4 * CDP_LEVELS * 5);
-    int32_t* sc[2] = { tab, tab + CDP_LEVELS * 5 };
-    int32_t* rc[2] = { tab + 2 * CDP_LEVELS * 5, tab + 3 * CDP_LEVELS * 5 };
+    int32_t* gtab = lvl_scratch + (size_t)b * (4 * CDP_LEVELS * 5);
+    auto SC = [&](const int which, const int idx) -> int32_t* {
+        return idx < CDP_SL * 5 ? &s_sc[wib][which][idx] : gtab + which * (CDP_LEVELS * 5) + idx;
+    };
+    auto RC = [&](const int which, const int idx) -> int32_t* {
+        return idx < CDP_SL * 5 ? &s_rc[wib][which][idx] : gtab + (2 + which) * (CDP_LEVELS * 5) + idx;
+    };
     int cur = 0;
 
     // record 0 is reserved for column (0,0,'A'): the target of floored columns' best_p = (0,0,0)
-    recs[0].pred = 0; recs[0].info = 0; recs[0].score2 = -2;
+    if (lane == 0) { recs[0].pred = 0; recs[0].info = 0; recs[0].score2 = -2; }
     uint32_t nrec = 1;
     int g_best2 = -2, g_rec = -1, g_ck = 0;
     int err = 0;
     const uint2* slots = slot_arena + bd.slot_off * VSLOT;
+    // two positions (32 uint2 = 256 bytes) per load: lanes 0-15 position i0, lanes 16-31 position i0 + 1
+    auto load2 = [&](const int i0) -> uint2 {
+        const int i = i0 + (lane >> 4);
+        return i < i_hi ? __ldg(slots + (size_t)i * VSLOT + (lane & 15)) : make_uint2(0u, 0u);
+    };
+    uint2 v0 = load2(i_lo), v1 = load2(i_lo + 2), v2 = load2(i_lo + 4);
 
-    for (int i = i_lo; i < i_hi; i++) {
-        const uint2* slot = slots + (size_t)i * VSLOT;
-        const uint2 hd = slot[0];
-        const int n = (int)(hd.x >> 16), coverage = (int)(hd.x & 0xffffu);
+    for (int i0 = i_lo; i0 < i_hi; i0 += 2) {
+      const uint2 v = v0; v0 = v1; v1 = v2; v2 = load2(i0 + 6);
+#pragma unroll 1
+      for (int half = 0; half < 2; half++) {
+        const int i = i0 + half;
+        if (i >= i_hi) break;
+        const int basel = half * 16;
+        const uint32_t hx = __shfl_sync(FULL, v.x, basel), hy = __shfl_sync(FULL, v.y, basel);
+        const int n = (int)(hx >> 16), coverage = (int)(hx & 0xffffu);
         const int hi_flag = ((unsigned)coverage > min_cov) ? (int)0x80000000 : 0;
-        if (i == 0) recs[0].info = hi_flag;
+        if (i == 0 && lane == 0) recs[0].info = hi_flag;
+        // links 0..14 of the position sit in the slot; lane e < 15 takes link e
+        const uint32_t sx = __shfl_sync(FULL, v.x, (basel + 1 + lane) & 31), sy = __shfl_sync(FULL, v.y, (basel + 1 + lane) & 31);
         if (coverage == 0) { cur ^= 1; continue; }
-        const uint2* ovf = ovf_arena + hd.y;
-        int32_t* psc = sc[cur ^ 1]; int32_t* prc = rc[cur ^ 1];
-        int32_t* csc = sc[cur]; int32_t* crc = rc[cur];
-        int e = 0;
-        int lev = 0;
-        while (e < n) {
-            // ---- one delta level: links of its (up to five) columns, interleaved in first-appearance order
-            int best[5], bpred[5], bck[5], nl[5];
-#pragma unroll
-            for (int k = 0; k < 5; k++) { best[k] = INT_MIN; bpred[k] = -1; bck[k] = 0; nl[k] = 0; }
-            const int32_t* ssc = lev == 0 ? psc : csc;        // predecessor columns: position i-1 for delta 0
-            const int32_t* src = lev == 0 ? prc : crc;
-            for (; e < n; e++) {
-                const uint2 lk = e < VSLOT - 1 ? slot[1 + e] : ovf[e - (VSLOT - 1)];
-                if ((int)(lk.x >> 16) != lev) break;
-                const int kk = (int)((lk.x >> 13) & 7u);
-                const uint32_t pred = lk.x & 0x1fffu;
-                int s2 = 2 * (int)lk.y - coverage, prj = -1;
-                if (pred != LK_START) {
-                    const int slotp = (int)(pred >> 3) * 5 + (int)(pred & 7u);
-                    s2 += ssc[slotp]; prj = src[slotp];
-                }
-#pragma unroll
-                for (int k = 0; k < 5; k++)
-                    if (k == kk) {
-                        if (nl[k] == 0 || s2 > best[k]) { best[k] = s2; bpred[k] = prj; bck[k] = nl[k]; }   // strict '>': first wins
-                        nl[k]++;
-                    }
-            }
-            // ---- close the level in base order: records, column scores, global best (falcon.c:420-469)
+        const uint2* ovf = ovf_arena + hy;
+
+        int best[5], bpred[5], bck[5], nl[5];
+        int lev = -1;                          // the open delta level
+        // ---- close a level in base order: records, column scores, global best (falcon.c:420-469)
+        auto close_level = [&]() {
 #pragma unroll
             for (int k = 0; k < 5; k++) {
                 if (nl[k] == 0) continue;      // dead column: never referenced (a link's predecessor column
@@ -228,13 +240,58 @@ k_cns_dp(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, const VoteMeta
                 uint32_t ridx;
                 if (i == 0 && lev == 0 && k == 0) ridx = 0; else { ridx = nrec; nrec++; }
                 if (ridx >= bd.rec_cap) { err = 2; ridx = bd.rec_cap - 1; }
-                recs[ridx].pred = col_pred; recs[ridx].info = hi_flag | (i << 3) | k; recs[ridx].score2 = col_sc2;
-                csc[lev * 5 + k] = col_sc2; crc[lev * 5 + k] = (int32_t)ridx;
+                if (lane == 0) {
+                    recs[ridx].pred = col_pred; recs[ridx].info = hi_flag | (i << 3) | k; recs[ridx].score2 = col_sc2;
+                    *SC(cur, lev * 5 + k) = col_sc2; *RC(cur, lev * 5 + k) = (int32_t)ridx;
+                }
                 if (col_sc2 > g_best2) { g_best2 = col_sc2; g_rec = (int)ridx; g_ck = best_ck; }
             }
-            lev++;      // levels are contiguous: every delta-d tag follows a delta-(d-1) tag of the same read
+            __syncwarp();                      // the next level (or position) reads these columns
+        };
+        for (int e0 = 0; e0 < n; e0 += 32) {
+            const int e = e0 + lane;
+            const bool valid = e < n;
+            uint32_t kx = sx, ky = sy;
+            if (valid && e >= VSLOT - 1) { const uint2 o = ovf[e - (VSLOT - 1)]; kx = o.x; ky = o.y; }
+            const int lev_e = valid ? (int)(kx >> 16) : INT_MAX;
+            const int kk = (int)((kx >> 13) & 7u);
+            const uint32_t pred = kx & 0x1fffu;
+            const int lev_lo = __shfl_sync(FULL, lev_e, 0), lev_hi = __shfl_sync(FULL, lev_e, min(32, n - e0) - 1);
+            // links are sorted by level and levels are contiguous: every delta-d tag follows a
+            // delta-(d-1) tag of the same read
+            for (int L = lev_lo; L <= lev_hi; L++) {
+                if (L != lev) {
+                    if (lev >= 0) close_level();
+                    lev = L;
+#pragma unroll
+                    for (int k = 0; k < 5; k++) { best[k] = INT_MIN; bpred[k] = -1; bck[k] = 0; nl[k] = 0; }
+                }
+                const bool mine = valid && lev_e == L;
+                int s2 = 2 * (int)ky - coverage, prj = -1;
+                if (mine && pred != LK_START) {
+                    const int slotp = (int)(pred >> 3) * 5 + (int)(pred & 7u);
+                    const int which = L == 0 ? (cur ^ 1) : cur;       // predecessor columns: position i-1 for delta 0
+                    s2 += *SC(which, slotp); prj = *RC(which, slotp);
+                }
+#pragma unroll
+                for (int k = 0; k < 5; k++) {
+                    const bool in_col = mine && kk == k;
+                    const unsigned m = __ballot_sync(FULL, in_col);
+                    if (m == 0u) continue;
+                    const int cand = in_col ? s2 : INT_MIN;
+                    const int cb = __reduce_max_sync(FULL, cand);
+                    if (nl[k] == 0 || cb > best[k]) {                 // strict '>': the first link wins ties
+                        const int wl = __ffs(__ballot_sync(FULL, in_col && cand == cb)) - 1;
+                        best[k] = cb; bpred[k] = __shfl_sync(FULL, prj, wl);
+                        bck[k] = nl[k] + __popc(m & ((1u << wl) - 1u));
+                    }
+                    nl[k] += __popc(m);
+                }
+            }
         }
+        if (lev >= 0) close_level();
         cur ^= 1;
+      }
     }
     // ------------------------------------------------------------ backtrack (falcon.c:479-542)
     // The string is produced back to front; it is written from the END of the block's output area
@@ -243,11 +300,27 @@ k_cns_dp(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, const VoteMeta
     const int cap = 2 * t_len + 4;
     int pos = cap;                                // one past the last byte written so far
     if (err == 0) {
-        char bb = '$'; int ck = g_ck; int rcur = g_rec;
+        int32_t* win = s_win[wib];
+        int wlo = 0, whi = -1;                    // the window holds records wlo..whi
+        auto fetch = [&](const int r, int& r_pred, int& r_info, int& r_sc) {
+            if (r < wlo || r > whi) {
+                __syncwarp();
+                whi = r; wlo = max(0, r - (CDP_WIN - 1));
+                const int32_t* src = reinterpret_cast<const int32_t*>(recs + wlo);
+                const int nw = (whi - wlo + 1) * 3;
+                for (int j = lane; j < nw; j += 32) win[j] = src[j];
+                __syncwarp();
+            }
+            const int o = (r - wlo) * 3;
+            r_pred = win[o]; r_info = win[o + 1]; r_sc = win[o + 2];
+        };
+        __syncwarp();                             // lane 0's record stores are visible to every lane
+        char bb = '$'; int ck = g_ck;
         unsigned index = 0; const unsigned lim = (unsigned)t_len * 2u;
+        int r_pred, r_info, r_sc;
+        fetch(g_rec, r_pred, r_info, r_sc);
         for (;;) {
-            const CnsRec r = recs[rcur];
-            const bool hi = r.info < 0;
+            const bool hi = r_info < 0;
             switch (ck) {
                 case 0: bb = hi ? 'A' : 'a'; break;
                 case 1: bb = hi ? 'C' : 'c'; break;
@@ -256,20 +329,21 @@ k_cns_dp(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, const VoteMeta
                 case 4: bb = '-'; break;
                 default: break;
             }
-            if (r.pred == -1 || index >= lim) break;
-            const CnsRec pr = recs[r.pred];
+            if (r_pred == -1 || index >= lim) break;
+            int p_pred, p_info, p_sc;
+            fetch(r_pred, p_pred, p_info, p_sc);
             if (bb != '-') {
-                pos--; cns[pos] = bb;
-                if (want_eqv) eqv[pos] = r.score2 / 2 - pr.score2 / 2;
+                pos--;
+                if (lane == 0) { cns[pos] = bb; if (want_eqv) eqv[pos] = r_sc / 2 - p_sc / 2; }
                 index++;
             }
-            ck = pr.info & 7;
-            rcur = r.pred;
+            ck = p_info & 7;
+            r_pred = p_pred; r_info = p_info; r_sc = p_sc;
         }
-        cns[cap] = 0;
+        if (lane == 0) cns[cap] = 0;
     }
     co.len = cap - pos; co.start = pos; co.err = err;
-    out[b] = co;
+    if (lane == 0) out[b] = co;
 }
 
 }  // namespace fcx
