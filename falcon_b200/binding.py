@@ -113,6 +113,9 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
                                          C.POINTER(C.c_void_p)]
     lib.fcx_last_pair_info.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     lib.fcx_last_stats.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+    lib.fcx_trim_blocks.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_uint,
+                                    C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint32)]
+    lib.fcx_pool_truncate.argtypes = [C.c_void_p, C.c_uint32]
     lib.fcx_align_pairs.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.fcx_multi_create.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]
     lib.fcx_multi_destroy.argtypes = [C.c_void_p]
@@ -286,6 +289,27 @@ class Engine:
         data, off = self.consensus_blocks_raw(block_off, ids, min_cov, min_idt, K)
         raw = data.tobytes()
         return [raw[int(off[i]):int(off[i + 1])] for i in range(len(blocks))]
+
+    def trim_blocks_raw(self, block_off: np.ndarray, read_ids: np.ndarray, edge_tolerance: int = 1000,
+                        trim_size: int = 50, max_n_read: int = 500, max_cov_aln: int = 0):
+        """--trim on the device (get_consensus_with_trim, consensus.py:123-147): appends the trimmed
+        reads to the pool and returns the new (block_off, read_ids)."""
+        block_off = np.ascontiguousarray(block_off, dtype=np.uint32)
+        read_ids = np.ascontiguousarray(read_ids, dtype=np.uint32)
+        nb = block_off.shape[0] - 1
+        ob, oi, nr = C.c_void_p(), C.c_void_p(), C.c_uint32()
+        self._check(self._lib.fcx_trim_blocks(self._h, nb, block_off.ctypes.data, read_ids.ctypes.data,
+                                              edge_tolerance, trim_size, max_n_read, max_cov_aln,
+                                              C.byref(ob), C.byref(oi), C.byref(nr)), "fcx_trim_blocks")
+        new_off = np.ctypeslib.as_array((C.c_uint32 * (nb + 1)).from_address(ob.value)).copy()
+        n_ids = int(new_off[-1])
+        new_ids = np.ctypeslib.as_array((C.c_uint32 * max(1, n_ids)).from_address(oi.value)).copy()[:n_ids]
+        self.n_reads = int(nr.value)
+        return new_off, new_ids
+
+    def pool_truncate(self, n_reads: int):
+        self._check(self._lib.fcx_pool_truncate(self._h, n_reads), "fcx_pool_truncate")
+        self.n_reads = n_reads
 
     def generate_consensus(self, seqs: Sequence[bytes], min_cov: int, min_idt: float, K: int = 8) -> bytes:
         """One seed block given as sequences (seqs[0] = seed), like the reference call."""

@@ -8,6 +8,7 @@
 // kernels of one wave (k_consensus: one warp per block, a serial chain over the seed) overlap the
 // issue-bound kernels of another (k_dp), which is where the throughput comes from.
 #include "fcx_kernels.cuh"
+#include "fcx_trim.cuh"
 #include "../../include/falcon_b200.h"
 
 #include <algorithm>
@@ -122,6 +123,9 @@ struct fcx_ctx {
     int dp_variant = 3;                // 3: k_dp3 (default); 1: k_dp (round-1 kernel); 2: k_dp with TMA-staged spans
     uint32_t debug_split_above = 0;    // test hook: pretend waves with more blocks than this do not fit
     bool debug_tiny_capacity = false;  // test hook: start every wave with arenas that are too small
+    // --trim: block lists of the last fcx_trim_blocks call
+    std::vector<uint32_t> trim_block_off, trim_read_ids;
+    DevBuf d_trim_scratch, d_trim_out, d_subs, d_sub_wb;
 };
 
 static thread_local std::string g_create_err;
@@ -223,7 +227,8 @@ extern "C" void fcx_destroy(fcx_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     DevBuf* bufs[] = {&ctx->d_pool, &ctx->d_ascii, &ctx->d_aoff, &ctx->d_woff, &ctx->d_len, &ctx->d_dirty,
-                      &ctx->d_trace1, &ctx->d_path1, &ctx->d_aln1, &ctx->d_str1};
+                      &ctx->d_trace1, &ctx->d_path1, &ctx->d_aln1, &ctx->d_str1,
+                      &ctx->d_trim_scratch, &ctx->d_trim_out, &ctx->d_subs, &ctx->d_sub_wb};
     for (auto* b : bufs) b->release();
     for (auto& L : ctx->lanes) L.release();
     for (auto& ev : ctx->tev) if (ev) cudaEventDestroy(ev);
@@ -796,6 +801,172 @@ extern "C" int fcx_timer_stop(fcx_ctx* ctx, double* ms) {
 extern "C" int fcx_internal_want_eqv(fcx_ctx* ctx, int on) { ctx->want_eqv = on != 0; return 0; }
 extern "C" int fcx_internal_last_eqv(fcx_ctx* ctx, const int32_t** eqv, uint64_t* n) {
     *eqv = ctx->out_eqv.data(); *n = ctx->out_eqv.size(); return 0;
+}
+
+// ---------------------------------------------------------------------------------- --trim
+// get_consensus_with_trim (falcon_kit/mains/consensus.py:123-158) for a batch of seed blocks: the
+// per-read k-mer chaining runs on the device (k_trim_range), the scalar post-processing of
+// get_alignment (:62-99) and the read selection (:131-147) are a few integer operations per read
+// on the host, and the trimmed reads are cut out of the packed pool on the device (k_subreads) and
+// APPENDED to the pool as new reads.  Returns the new block lists (seed first, then the trimmed
+// reads, longest alignment first), ready for fcx_consensus_blocks.
+extern "C" int fcx_trim_blocks(fcx_ctx* ctx, uint32_t n_blocks, const uint32_t* block_off, const uint32_t* read_ids,
+                               int edge_tolerance, int trim_size, unsigned max_n_read, unsigned max_cov_aln,
+                               const uint32_t** out_block_off, const uint32_t** out_read_ids, uint32_t* out_n_reads) {
+    CK(cudaSetDevice(ctx->device));
+    ctx->trim_block_off.assign(1, 0u); ctx->trim_read_ids.clear();
+    for (uint32_t b = 0; b < n_blocks; b++) {
+        if (block_off[b + 1] <= block_off[b]) { ctx->err = "empty block (a block needs at least the seed)"; return 1; }
+        for (uint32_t i = block_off[b]; i < block_off[b + 1]; i++) {
+            if (read_ids[i] >= ctx->n_reads) { ctx->err = "read id outside the uploaded pool"; return 1; }
+            if (ctx->h_len[read_ids[i]] > 100000) { ctx->err = "read longer than 100000 bases in a seed block"; return 1; }
+        }
+    }
+    Lane& L = ctx->lanes[0];
+    cudaStream_t st = L.stream;
+    struct Cut { uint32_t src; int32_t s, e; };
+    std::vector<SubRead> subs; std::vector<uint64_t> sub_wb;
+    std::vector<int32_t> new_len; std::vector<uint64_t> new_woff;
+    uint64_t w_next = ctx->h_woff[ctx->n_reads], wb = 0;
+    uint32_t next_id = ctx->n_reads;
+    const uint32_t chunk = std::max(1u, ctx->max_wave_blocks);
+    for (uint32_t b0 = 0; b0 < n_blocks; b0 += chunk) {
+        const uint32_t b1 = std::min(n_blocks, b0 + chunk), nb = b1 - b0;
+        std::vector<BlockDesc> hb(nb);
+        uint64_t npairs64 = 0, kpos_total = 0; int max_slen = 1, max_rlen = 1;
+        for (uint32_t b = 0; b < nb; b++) {
+            const uint32_t lo = block_off[b0 + b], hi = block_off[b0 + b + 1];
+            BlockDesc& d = hb[b];
+            memset(&d, 0, sizeof d);
+            const uint32_t seed = read_ids[lo];
+            d.seed_woff = ctx->h_woff[seed]; d.slen = ctx->h_len[seed];
+            d.pair_begin = (uint32_t)npairs64; d.n_pairs = hi - lo - 1;
+            d.kpos_off = kpos_total; kpos_total += (uint64_t)std::max(d.slen, 1);
+            npairs64 += d.n_pairs; max_slen = std::max(max_slen, d.slen);
+        }
+        const uint32_t np = (uint32_t)npairs64;
+        std::vector<PairDesc> hp(np);
+        for (uint32_t b = 0; b < nb; b++)
+            for (uint32_t j = 0; j < hb[b].n_pairs; j++) {
+                const uint32_t rid = read_ids[block_off[b0 + b] + 1 + j];
+                PairDesc& pd = hp[hb[b].pair_begin + j];
+                pd.read_woff = ctx->h_woff[rid]; pd.block = b; pd.rlen = ctx->h_len[rid];
+                max_rlen = std::max(max_rlen, pd.rlen);
+            }
+        std::vector<TrimOut> ho(np);
+        if (np) {
+            CK(L.d_blocks.reserve(nb * sizeof(BlockDesc)));
+            CK(L.d_pairs.reserve((size_t)np * sizeof(PairDesc)));
+            CK(L.d_ktab.reserve((size_t)nb * KTAB * 4));
+            CK(L.d_kpos.reserve(kpos_total * 4 + 16));
+            CK(L.d_kbits.reserve((size_t)nb * (KTAB / 32) * 4));
+            CK(L.d_counter.reserve(64));
+            CK(ctx->d_trim_out.reserve((size_t)np * sizeof(TrimOut)));
+            // per-warp scratch: at most TRIM_MASK_TH hits per query k-mer
+            const uint32_t list_cap = (uint32_t)(((size_t)TRIM_MASK_TH * ((size_t)max_rlen / 4 + 2) + 63) & ~(size_t)31);
+            const uint32_t hist_cap = (uint32_t)(((size_t)max_rlen + max_slen + 72) & ~(size_t)31);
+            const size_t per_warp = ((size_t)5 * list_cap + hist_cap) * 4;
+            unsigned grid = std::min<unsigned>((np + TRIM_WARPS - 1) / TRIM_WARPS, (unsigned)ctx->sm_count * 4u);
+            while (grid > 1 && (size_t)grid * TRIM_WARPS * per_warp > ((size_t)8 << 30)) grid /= 2;
+            CK(ctx->d_trim_scratch.reserve((size_t)grid * TRIM_WARPS * per_warp));
+            CK(cudaMemcpyAsync(L.d_blocks.p, hb.data(), nb * sizeof(BlockDesc), cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(L.d_pairs.p, hp.data(), (size_t)np * sizeof(PairDesc), cudaMemcpyHostToDevice, st));
+            CK(cudaMemsetAsync(L.d_ktab.p, 0, (size_t)nb * KTAB * 4, st));
+            CK(cudaMemsetAsync(L.d_counter.p, 0, 64, st));
+            FCX_LAUNCH(k_index, nb, 256, 0, st, L.d_blocks.as<BlockDesc>(), ctx->d_pool.as<uint32_t>(), L.d_ktab.as<uint32_t>(),
+                       L.d_kpos.as<uint32_t>(), L.d_kbits.as<uint32_t>());
+            FCX_LAUNCH(k_trim_range, grid, TRIM_WARPS * 32, 0, st, L.d_blocks.as<BlockDesc>(), L.d_pairs.as<PairDesc>(), np,
+                       ctx->d_pool.as<uint32_t>(), L.d_ktab.as<uint32_t>(), L.d_kpos.as<uint32_t>(),
+                       ctx->d_trim_scratch.as<uint32_t>(), list_cap, hist_cap, L.d_counter.as<uint32_t>(),
+                       ctx->d_trim_out.as<TrimOut>());
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(ho.data(), ctx->d_trim_out.p, (size_t)np * sizeof(TrimOut), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+        }
+        // ---- get_alignment's scalar tail (consensus.py:62-99) and the selection (:131-147)
+        for (uint32_t b = 0; b < nb; b++) {
+            const uint32_t lo = block_off[b0 + b];
+            const uint32_t seed = read_ids[lo];
+            const int len_0 = ctx->h_len[seed];
+            std::vector<Cut> cuts;
+            for (uint32_t j = 0; j < hb[b].n_pairs; j++) {
+                const TrimOut& t = ho[hb[b].pair_begin + j];
+                const uint32_t rid = read_ids[lo + 1 + j];
+                const int len_1 = ctx->h_len[rid];
+                int s1 = t.s1, e1 = t.e1 + KMER + KMER / 2, s0 = t.s2, e0 = t.e2 + KMER + KMER / 2;
+                e1 = std::min(e1, len_1); e0 = std::min(e0, len_0);
+                int aln_size = 1; long aln_score = 0;
+                if (e1 - s1 > 500) { aln_size = std::max(e1 - s1, e0 - s0); aln_score = (long)t.score * 48; }
+                if (s1 > edge_tolerance && s0 > edge_tolerance) continue;
+                if (len_1 - e1 > edge_tolerance && len_0 - e0 > edge_tolerance) continue;
+                if (!(e1 - s1 > 500 && aln_size > 500)) continue;
+                if (aln_score > 1000 && e1 - s1 > 500) cuts.push_back(Cut{rid, s1 + trim_size, e1 - trim_size});
+            }
+            std::stable_sort(cuts.begin(), cuts.end(), [](const Cut& a, const Cut& c) { return a.e - a.s > c.e - c.s; });   // longest first
+            size_t keep = cuts.size();
+            if (cuts.size() > max_n_read) {                       // get_longest_reads(.., sort=False), consensus.py:26-45
+                size_t longest = max_n_read;
+                if (max_cov_aln > 0) {
+                    longest = 1; long read_cov = 0;
+                    for (const Cut& c : cuts) {
+                        if (len_0 > 0 && read_cov / len_0 > (long)max_cov_aln) break;
+                        longest++; read_cov += std::max(0, c.e - c.s);
+                    }
+                    longest = std::min<size_t>(longest, max_n_read);
+                }
+                keep = longest > 0 ? longest - 1 : 0;               // seqs[:longest] includes the seed
+            }
+            ctx->trim_read_ids.push_back(seed);
+            for (size_t c = 0; c < keep; c++) {
+                const int len = std::max(0, cuts[c].e - cuts[c].s);   // Python slice semantics: empty if e <= s
+                SubRead sr; sr.src_woff = ctx->h_woff[cuts[c].src]; sr.dst_woff = w_next; sr.s = len ? cuts[c].s : 0; sr.len = len;
+                const uint64_t words = (((uint64_t)len + 15) / 16 + 1 + 3) & ~(uint64_t)3;
+                subs.push_back(sr); sub_wb.push_back(wb);
+                new_len.push_back(len); new_woff.push_back(w_next);
+                w_next += words; wb += words;
+                ctx->trim_read_ids.push_back(next_id++);
+            }
+            ctx->trim_block_off.push_back((uint32_t)ctx->trim_read_ids.size());
+        }
+    }
+    // ---- append the trimmed reads to the pool
+    if (!subs.empty()) {
+        const size_t need = (w_next + 4) * 4;
+        if (need > ctx->d_pool.cap) {                               // grow, keeping the packed reads
+            DevBuf bigger;
+            CK(bigger.reserve(need + need / 4));
+            CK(cudaMemcpyAsync(bigger.p, ctx->d_pool.p, (ctx->h_woff[ctx->n_reads] + 4) * 4, cudaMemcpyDeviceToDevice, st));
+            CK(cudaStreamSynchronize(st));
+            ctx->d_pool.release();
+            ctx->d_pool = bigger;
+        }
+        CK(ctx->d_subs.reserve(subs.size() * sizeof(SubRead)));
+        CK(ctx->d_sub_wb.reserve((sub_wb.size() + 1) * 8));
+        CK(cudaMemcpyAsync(ctx->d_subs.p, subs.data(), subs.size() * sizeof(SubRead), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->d_sub_wb.p, sub_wb.data(), sub_wb.size() * 8, cudaMemcpyHostToDevice, st));
+        FCX_LAUNCH(k_subreads, (unsigned)((wb + 255) / 256), 256, 0, st, ctx->d_subs.as<SubRead>(), (uint32_t)subs.size(),
+                   ctx->d_sub_wb.as<uint64_t>(), wb, ctx->d_pool.as<uint32_t>());
+        CK(cudaGetLastError());
+        CK(cudaMemsetAsync((char*)ctx->d_pool.p + w_next * 4, 0, 16, st));
+        CK(cudaStreamSynchronize(st));
+        ctx->h_woff.pop_back();
+        for (size_t i = 0; i < subs.size(); i++) { ctx->h_woff.push_back(new_woff[i]); ctx->h_len.push_back(new_len[i]); }
+        ctx->h_woff.push_back(w_next);
+        ctx->n_reads = ctx->n_reserved = next_id;
+    }
+    *out_block_off = ctx->trim_block_off.data();
+    *out_read_ids = ctx->trim_read_ids.data();
+    if (out_n_reads) *out_n_reads = ctx->n_reads;
+    return 0;
+}
+
+// Drop the reads appended by fcx_trim_blocks (or any tail of the pool): the pool keeps its first n reads.
+extern "C" int fcx_pool_truncate(fcx_ctx* ctx, uint32_t n_reads) {
+    if (n_reads > ctx->n_reads) { ctx->err = "fcx_pool_truncate: the pool holds fewer reads"; return 1; }
+    ctx->h_woff.resize((size_t)n_reads + 1);
+    ctx->h_len.resize(n_reads);
+    ctx->n_reads = ctx->n_reserved = n_reads;
+    return 0;
 }
 
 // Batched banded alignment of pool sequences (distance only), for stage-2 style callers:

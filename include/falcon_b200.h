@@ -210,6 +210,21 @@ typedef struct { int32_t aln_str_size, dist, aln_q_e, aln_t_e; } fcx_align_resul
 int fcx_align_pairs(fcx_ctx *, uint32_t n_pairs, const uint32_t *q_ids, const uint32_t *t_ids,
                     const int32_t *ranges, int band_tolerance, fcx_align_result *out);
 
+/* --trim (falcon_kit/mains/consensus.py:123-158, get_consensus_with_trim) for a batch of seed
+ * blocks.  For every non-seed read the k-mer chaining of get_alignment (consensus.py:48-99:
+ * mask_k_mer(.., 16), find_kmer_pos_for_seq, find_best_aln_range2(K, 400, 25); src/c/kmer_lookup.c:
+ * 195-204, 207-286, 429-585) runs on the device; reads are kept / cut by the reference's rules
+ * (aln_score > 1000, span > 500, edge_tolerance, trim_size off both ends), ordered longest
+ * alignment first, capped like get_longest_reads(.., sort=False); the trimmed reads are cut out of
+ * the packed pool on the device and APPENDED to it as new reads.  Returns new block lists in the
+ * shape fcx_consensus_blocks accepts (owned by the engine, valid until the next fcx_trim_blocks)
+ * and the new pool size.  fcx_pool_truncate(n) drops everything after the first n reads again. */
+int fcx_trim_blocks(fcx_ctx *, uint32_t n_blocks, const uint32_t *block_off, const uint32_t *read_ids,
+                    int edge_tolerance, int trim_size, unsigned max_n_read, unsigned max_cov_aln,
+                    const uint32_t **out_block_off, const uint32_t **out_read_ids,
+                    uint32_t *out_n_reads);
+int fcx_pool_truncate(fcx_ctx *, uint32_t n_reads);
+
 /* ---- several GPUs in one process -------------------------------------------
  * A fcx_multi owns one engine per listed device.  fcx_multi_pool_upload gives EVERY device the whole
  * 2-bit read store: device d packs 1/N of the reads from host memory, the other devices receive that

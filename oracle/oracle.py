@@ -137,6 +137,9 @@ class Ref:
         lib.find_kmer_pos_for_seq.restype = C.POINTER(_KmerMatch)
         lib.find_best_aln_range.argtypes = [C.POINTER(_KmerMatch), C.c_int, C.c_int, C.c_int]
         lib.find_best_aln_range.restype = C.POINTER(_AlnRange)
+        lib.find_best_aln_range2.argtypes = [C.POINTER(_KmerMatch), C.c_int, C.c_int, C.c_int]
+        lib.find_best_aln_range2.restype = C.POINTER(_AlnRange)
+        lib.mask_k_mer.argtypes = [C.c_int, C.POINTER(_KmerLookup), C.c_int]
         lib.free_kmer_match.argtypes = [C.POINTER(_KmerMatch)]
         lib.free_aln_range.argtypes = [C.POINTER(_AlnRange)]
         lib.free_kmer_lookup.argtypes = [C.POINTER(_KmerLookup)]
@@ -165,6 +168,26 @@ class Ref:
         km = lib.find_kmer_pos_for_seq(read, len(read), K, sda, lk)
         n_match = km[0].count
         ar = lib.find_best_aln_range(km, K, K * 6, 5)
+        res = (n_match, ar[0].s1, ar[0].e1, ar[0].s2, ar[0].e2, ar[0].score)
+        lib.free_aln_range(ar)
+        lib.free_kmer_match(km)
+        lib.free_seq_addr_array(sda)
+        lib.free_seq_array(sa)
+        lib.free_kmer_lookup(lk)
+        return res
+
+    def trim_range(self, read: bytes, seed: bytes, K: int = 8):
+        """The C calls of get_alignment (falcon_kit/mains/consensus.py:50-63): masked k-mer hits and
+        find_best_aln_range2(K, K * 50, 25) -> (n_match, s1, e1, s2, e2, score), raw."""
+        lib = self.lib
+        lk = lib.allocate_kmer_lookup(1 << (2 * K))
+        sa = lib.allocate_seq(len(seed))
+        sda = lib.allocate_seq_addr(len(seed))
+        lib.add_sequence(0, K, seed, len(seed), sda, sa, lk)
+        lib.mask_k_mer(1 << (2 * K), lk, 16)
+        km = lib.find_kmer_pos_for_seq(read, len(read), K, sda, lk)
+        n_match = km[0].count
+        ar = lib.find_best_aln_range2(km, K, K * 50, 25)
         res = (n_match, ar[0].s1, ar[0].e1, ar[0].s2, ar[0].e2, ar[0].score)
         lib.free_aln_range(ar)
         lib.free_kmer_match(km)

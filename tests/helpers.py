@@ -9,8 +9,9 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 class OracleEngine:
     """Same surface as falcon_b200.binding.Engine, arithmetic by the CPU oracle (tests only)."""
 
-    def __init__(self, oracle):
+    def __init__(self, oracle, ref=None):
         self.oracle = oracle
+        self.ref = ref          # compiled reference: needed only for --trim (k-mer chaining)
         self.pool = []
 
     def upload_pool(self, reads):
@@ -34,15 +35,52 @@ class OracleEngine:
         return np.frombuffer(b"".join(cns), dtype=np.uint8), off
 
 
+    def trim_blocks_raw(self, block_off, read_ids, edge_tolerance, trim_size, max_n_read, max_cov_aln):
+        """Stand-in for fcx_trim_blocks: the reference's own logic (tests/ref_host.py)."""
+        import numpy as np
+        import ref_host
+        cfg = (0, 8, max_n_read, 0.7, edge_tolerance, trim_size, 0, max_cov_aln)
+        new_off, new_ids = [0], []
+        for b in range(len(block_off) - 1):
+            seqs = [self.pool[i] for i in read_ids[int(block_off[b]):int(block_off[b + 1])]]
+            out = ref_host.trim_block(self.ref, seqs, cfg)
+            new_ids.append(int(read_ids[int(block_off[b])]))
+            for sq in out[1:]:
+                self.pool.append(sq)
+                new_ids.append(len(self.pool) - 1)
+            new_off.append(len(new_ids))
+        return np.asarray(new_off, dtype=np.uint32), np.asarray(new_ids, dtype=np.uint32)
+
+
 def golden_cases():
     return json.load(open(os.path.join(GOLDEN, "manifest.json")))
 
 
-def run_cli(argv, stdin_bytes, engine, python_parser=False):
+def run_cli(argv, stdin_bytes, engine):
     from falcon_b200 import consensus
-    args = consensus.parse_args(["consensus"] + list(argv) + (["--python-parser"] if python_parser else []))
+    args = consensus.parse_args(["consensus"] + list(argv))
     out = io.StringIO()
     consensus.run(args, stdin=io.BytesIO(stdin_bytes), stdout=out, engine=engine)
+    return out.getvalue().encode()
+
+
+def run_cli_python_host(argv, stdin_bytes, engine, ref=None):
+    """The same CLI contract with the host side done by tests/ref_host.py (Python restatement of the
+    reference's parser / read selection / trim): the checker for the native parser path."""
+    import ref_host
+    from falcon_b200 import consensus
+    args = consensus.parse_args(["consensus"] + list(argv))
+    cfg = (args.min_cov, 8, args.max_n_read, args.min_idt, args.edge_tolerance, args.trim_size,
+           args.min_cov_aln, args.max_cov_aln)
+    out = io.StringIO()
+    for seqs, seed_id in ref_host.get_seq_data(io.BytesIO(stdin_bytes), cfg, args.min_n_read, args.min_len_aln):
+        if args.trim:
+            seqs = ref_host.trim_block(ref, seqs, cfg)
+        elif len(seqs) > args.max_n_read:
+            seqs = ref_host.get_longest_reads(seqs, args.max_n_read, args.max_cov_aln, sort=True)
+        engine.upload_pool(seqs)
+        cns = engine.consensus_blocks([list(range(len(seqs)))], args.min_cov, args.min_idt)[0]
+        consensus.emit(out, cns.decode(), seed_id, args)
     return out.getvalue().encode()
 
 

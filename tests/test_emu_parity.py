@@ -194,3 +194,10 @@ def test_batched_align_pairs(emu, oracle):
             assert (got[1], got[2], got[3]) == (o["dist"], o["q_e"], o["t_e"])
     many = emu.align_pairs([0, 0, 1], [1, 1, 0], None, 1500)
     assert (many[0] == many[1]).all() and many[0][0] > 0
+
+
+def test_device_trim_vs_reference(emu, ref):
+    """k_trim_range / k_subreads / fcx_trim_blocks against the compiled reference's --trim logic."""
+    G._check_trim(emu, ref, synth.make_set(30000, 3000, 14, seed=21, n_blocks=3))
+    G._check_trim(emu, ref, synth.make_set(30000, 2500, 20, seed=23, n_blocks=2, len_sigma=0.4), edge_tolerance=500,
+                  trim_size=80, max_n_read=6, max_cov_aln=2)

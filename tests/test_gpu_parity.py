@@ -293,3 +293,33 @@ def test_deep_coverage_default_error_model(engine, oracle):
     got = engine.consensus_blocks([b.tolist() for b in S.blocks], 6, 0.70)
     for bi in range(len(S.blocks)):
         assert got[bi] == oracle.generate_consensus(S.block_seqs(bi), 6, 0.70)
+
+
+def _check_trim(engine, ref, S, edge_tolerance=1000, trim_size=50, max_n_read=500, max_cov_aln=0):
+    """fcx_trim_blocks (device chaining + sub-read cutting) vs the reference's get_consensus_with_trim
+    logic driven by the compiled reference (tests/ref_host.py): same reads, same order, same bytes --
+    checked through the consensus of the trimmed blocks, which must also equal the reference's."""
+    import ref_host
+    engine.upload_pool(S.pool)
+    n0 = engine.n_reads
+    block_off = np.zeros(len(S.blocks) + 1, dtype=np.uint32)
+    np.cumsum([len(b) for b in S.blocks], out=block_off[1:])
+    ids = np.concatenate(S.blocks).astype(np.uint32)
+    new_off, new_ids = engine.trim_blocks_raw(block_off, ids, edge_tolerance, trim_size, max_n_read, max_cov_aln)
+    cfg = (4, 8, max_n_read, 0.7, edge_tolerance, trim_size, 0, max_cov_aln)
+    want_blocks = [ref_host.trim_block(ref, S.block_seqs(bi), cfg) for bi in range(len(S.blocks))]
+    for bi, wb in enumerate(want_blocks):
+        assert int(new_off[bi + 1] - new_off[bi]) == len(wb), "block %d: number of trimmed reads" % bi
+        assert int(new_ids[int(new_off[bi])]) == int(S.blocks[bi][0])
+    got = engine.consensus_blocks([new_ids[int(new_off[b]):int(new_off[b + 1])].tolist() for b in range(len(S.blocks))], 4, 0.70)
+    for bi, wb in enumerate(want_blocks):
+        assert got[bi] == ref.generate_consensus(wb, 4, 0.70), "block %d: consensus of the trimmed block" % bi
+    assert sum(len(w) - 1 for w in want_blocks) > 0
+    engine.pool_truncate(n0)
+    assert engine.consensus_blocks([S.blocks[0].tolist()], 4, 0.70)[0] == ref.generate_consensus(S.block_seqs(0), 4, 0.70)
+
+
+def test_device_trim_vs_reference(engine, ref):
+    _check_trim(engine, ref, synth.make_set(60000, 5000, 25, seed=21, n_blocks=4))
+    _check_trim(engine, ref, synth.make_set(120000, 15000, 20, seed=22, n_blocks=3), edge_tolerance=600, trim_size=120)
+    _check_trim(engine, ref, synth.make_set(40000, 3000, 40, seed=23, n_blocks=3, len_sigma=0.4), max_n_read=10, max_cov_aln=3)

@@ -5,21 +5,22 @@ import os
 
 import pytest
 
-from helpers import GOLDEN, OracleEngine, golden_cases, run_cli
+from helpers import GOLDEN, OracleEngine, golden_cases, run_cli, run_cli_python_host
 
 CASES = golden_cases()
 
 
 @pytest.mark.parametrize("name", sorted(CASES))
-def test_cli_with_oracle_matches_reference_golden(name, oracle):
+def test_cli_with_oracle_matches_reference_golden(name, oracle, request):
     case = CASES[name]
+    ref = request.getfixturevalue("ref") if "--trim" in case["args"] else None
     stdin = open(os.path.join(GOLDEN, case["input"]), "rb").read()
     assert hashlib.md5(stdin).hexdigest() == case["in_md5"]
     want = open(os.path.join(GOLDEN, name + ".out"), "rb").read()
     assert hashlib.md5(want).hexdigest() == case["out_md5"]
-    got = run_cli(case["args"], stdin, OracleEngine(oracle))                       # native parser
+    got = run_cli(case["args"], stdin, OracleEngine(oracle, ref))                  # native parser
     assert got == want
-    got = run_cli(case["args"], stdin, OracleEngine(oracle), python_parser=True)   # Python restatement
+    got = run_cli_python_host(case["args"], stdin, OracleEngine(oracle, ref), ref)  # Python restatement of the host side
     assert got == want
 
 
@@ -44,7 +45,7 @@ def test_parser_block_rules():
     # consensus.py:161-209: 2-token lines only, '+' emits, '*' discards, '-' stops, dup ids dropped,
     # seed appended twice, >100000 cut to 99999
     import io
-    from falcon_b200 import consensus
+    import ref_host as consensus
     cfg = (4, 8, 500, 0.7, 1000, 50, 0, 0)
     long_seq = b"A" * 100005
     txt = b"s1 ACGT\nr1 AAAA\nr1 CCCC\nbad line here\nr2 GG\n+ +\nx1 TTTT\n* *\ny1 " + long_seq + b"\n+ +\n- -\nz1 ACGT\n+ +\n"
@@ -56,7 +57,7 @@ def test_parser_block_rules():
 
 def _python_blocks(txt, min_n_read, min_len_aln, max_n_read, min_cov_aln, max_cov_aln):
     import io
-    from falcon_b200 import consensus
+    import ref_host as consensus
     cfg = (4, 8, max_n_read, 0.7, 1000, 50, min_cov_aln, max_cov_aln)
     return [(sid, seqs) for seqs, sid in consensus.get_seq_data(io.BytesIO(txt), cfg, min_n_read, min_len_aln)]
 
