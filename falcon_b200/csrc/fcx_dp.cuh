@@ -293,7 +293,7 @@ k_dp3(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs,
     if (lane == 0) out[p] = res;
     __syncwarp();                       // wide mode: the ring is reused by the next pair; lane 0's trace records are visible
     // the backward walk of an accepted pair, while its last records are still in L2
-    if (res.accepted == 1) warp_walk_back(trace, path_arena + al.path_off, end_d, end_k, lane);
+    if (res.accepted == 1) { warp_walk_back(trace, path_arena + al.path_off, end_d, end_k, lane, s_V[wib]); __syncwarp(); }
   }
 }
 

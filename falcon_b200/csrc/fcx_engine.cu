@@ -208,7 +208,7 @@ extern "C" int fcx_create(int device, fcx_ctx** out) {
         if (!getenv("FCX_ARENA_GB")) ctx->arena_budget = std::min(ctx->arena_budget, (size_t)((double)free_b * 0.70));
     }
     CKC(cudaFuncSetAttribute(k_range, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (KTAB / 32) * 4 + RANGE_WARPS * RANGE_BINS * (int)sizeof(int)));
+                             (KTAB / 32) * 4 + 4 * RANGE_BINS * (int)sizeof(int) + 24 * 1024));
     ctx->lanes.resize(ctx->n_lanes);
     int prio_lo = 0, prio_hi = 0;
     CKC(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
@@ -439,11 +439,17 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
     if (np) {
         // histogram bins actually needed by this wave (diagonal range <= read + seed length)
         const int bins = std::min(RANGE_BINS, (max_rlen + max_slen) / BIN_SIZE + 8);
-        const size_t rsmem = (size_t)(KTAB / 32) * 4 + (size_t)RANGE_WARPS * bins * sizeof(int);
-        const unsigned per_sm = (unsigned)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / std::max<size_t>(rsmem, 1)));
+        // as many warps per CTA as the per-warp histograms allow (all on ONE seed block), at most two
+        // CTAs per SM: the 256 KB bucket tables in use at any time stay L2 resident
+        int rwarps = RANGE_WARPS_MAX;
+        while (rwarps > 4 && (size_t)(KTAB / 32) * 4 + (size_t)rwarps * bins * sizeof(int) > 96 * 1024) rwarps /= 2;
+        if (const char* e = getenv("FCX_RANGE_WARPS")) rwarps = std::max(1, std::min(RANGE_WARPS_MAX, atoi(e)));
+        const size_t rsmem = (size_t)(KTAB / 32) * 4 + (size_t)rwarps * bins * sizeof(int);
+        unsigned per_sm = (unsigned)std::max<size_t>(1, std::min<size_t>(2, (200 * 1024) / std::max<size_t>(rsmem, 1)));
+        if (const char* e = getenv("FCX_RANGE_CTAS")) per_sm = (unsigned)std::max(1, atoi(e));
         const unsigned rgrid = std::min<unsigned>(nb, (unsigned)ctx->sm_count * per_sm);
-        CKR(L.d_rlist.reserve((size_t)rgrid * RANGE_WARPS * RANGE_LIST_CAP * sizeof(uint32_t)));
-        FCX_LAUNCH(k_range, rgrid, RANGE_WARPS * 32, rsmem, st,
+        CKR(L.d_rlist.reserve((size_t)rgrid * rwarps * RANGE_LIST_CAP * sizeof(uint32_t)));
+        FCX_LAUNCH(k_range, rgrid, rwarps * 32, rsmem, st,
             L.d_blocks.as<BlockDesc>(), nb, L.d_pairs.as<PairDesc>(), pool, L.d_ktab.as<uint32_t>(),
             L.d_kpos.as<uint32_t>(), L.d_kbits.as<uint32_t>(), L.d_rlist.as<uint32_t>(), bins, L.d_ranges.as<PairRange>());
         CKL(cudaGetLastError());
@@ -676,7 +682,7 @@ extern "C" int fcx_consensus_blocks(fcx_ctx* ctx, uint32_t n_blocks, const uint3
             int slen = ctx->h_len[read_ids[lo]];
             const double mdiff = std::max(0.0, 1.0 - min_idt);
             const double capfrac = std::min(0.3, mdiff < 1.999 ? mdiff / (2.0 - mdiff) : 0.3);
-            double bb = (double)KTAB * 4 + (double)slen * (4 + (8 + (hi - lo - 1) / 16) * 12 + 2 * 5 + 16.0 * VSLOT * 1.5) + 4.0 * CDP_LEVELS * 5 * 4;
+            double bb = (double)KTAB * 4 + (double)slen * (4 + (8 + (hi - lo - 1) / 16) * 16 + 2 * 5 + 16.0 * VSLOT * 1.5) + 4.0 * CDP_LEVELS * 5 * 4;
             for (uint32_t i = lo + 1; i < hi; i++) {
                 // typical aligned span ~ 0.65 x the shorter sequence (exact sizes follow k_range;
                 // an under-estimate is caught by the out-of-memory split below)

@@ -25,7 +25,9 @@
 #define FCX_LAUNCH(kern, grid, block, smem, stream, ...) \
     emu::launch(emu::Dim3((unsigned)(grid)), emu::Dim3((unsigned)(block)), (size_t)(smem), [&]() { kern(__VA_ARGS__); })
 #define FCX_DYN_SHARED(type, name) type* name = reinterpret_cast<type*>(emu::g_cta->dyn_smem)
+#define FCX_NOINLINE __attribute__((noinline))
 #else
+#define FCX_NOINLINE __noinline__
 #define FCX_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define FCX_DYN_SHARED(type, name) extern __shared__ __align__(16) unsigned char name##_raw_[]; \
     type* name = reinterpret_cast<type*>(name##_raw_)
@@ -209,7 +211,7 @@ __global__ void __launch_bounds__(256) k_index(const BlockDesc* __restrict__ blo
 //           S_i - min_{j<=i} S_j, a reset happens exactly on a strict new prefix minimum, so
 //           (s1,s2) = coordinates of the FIRST arg-min of the prefix and (e1,e2) those of the
 //           first i attaining the overall maximum.
-constexpr int RANGE_WARPS = 4;
+constexpr int RANGE_WARPS_MAX = 16;     // warps per CTA are chosen per wave (shared-memory histogram size)
 constexpr int RANGE_BINS = 4224;   // >= (99999 + 99999) / 48 + 1
 
 // Slow path (match list does not fit the per-warp scratch): every pass re-walks the buckets.
@@ -349,9 +351,10 @@ __device__ __forceinline__ int rm_q(uint32_t m) { return (int)(m >> 17) << 2; }
 __device__ __forceinline__ int rm_t(uint32_t m) { return (int)(m & 0x1ffffu); }
 
 // Persistent CTAs, one seed block at a time: the block's non-empty-bucket bitmap (8 KB, from k_index)
-// sits in shared memory, its 256 KB bucket table and position list stay hot in L1/L2 because all
-// pairs of the block are looked up back to back by the four warps of one CTA.
-__global__ void __launch_bounds__(RANGE_WARPS * 32)
+// sits in shared memory, its 256 KB bucket table and position list stay hot in L2 because all
+// pairs of the block are looked up back to back by the (up to 16) warps of ONE CTA and only one or
+// two CTAs run per SM: the tables in use at any time (~150-300 x 256 KB) fit the 126 MB L2.
+__global__ void __launch_bounds__(RANGE_WARPS_MAX * 32)
 k_range(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, const PairDesc* __restrict__ pairs,
         const uint32_t* __restrict__ pool, const uint32_t* __restrict__ ktab,
         const uint32_t* __restrict__ kpos_arena, const uint32_t* __restrict__ kbits,
@@ -360,17 +363,18 @@ k_range(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, const PairDesc*
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     uint32_t* sbits = reinterpret_cast<uint32_t*>(s_dyn_all);                 // KTAB / 32 words
     int* hist = s_dyn_all + KTAB / 32 + wib * bins;      // bins >= (max read len + max seed len) / 48 + 2 for this wave
-    const uint32_t gw = blockIdx.x * RANGE_WARPS + wib;
+    const int n_warps = (int)(blockDim.x >> 5);
+    const uint32_t gw = blockIdx.x * n_warps + wib;
     uint32_t* list = list_scratch + (size_t)gw * RANGE_LIST_CAP;
     const unsigned lt = lanemask_lt();
   for (uint32_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
     const BlockDesc bd = blocks[blk];
     __syncthreads();                                     // every warp is done with the previous bitmap
-    for (int j = threadIdx.x; j < KTAB / 32; j += RANGE_WARPS * 32) sbits[j] = __ldg(kbits + (size_t)blk * (KTAB / 32) + j);
+    for (int j = threadIdx.x; j < KTAB / 32; j += (int)blockDim.x) sbits[j] = __ldg(kbits + (size_t)blk * (KTAB / 32) + j);
     __syncthreads();
     const uint32_t* tab = ktab + (size_t)blk * KTAB;
     const uint32_t* kpos = kpos_arena + bd.kpos_off;
-    for (uint32_t p = bd.pair_begin + wib; p < bd.pair_begin + bd.n_pairs; p += RANGE_WARPS) {
+    for (uint32_t p = bd.pair_begin + wib; p < bd.pair_begin + bd.n_pairs; p += n_warps) {
         const PairDesc pd = pairs[p];
         const uint32_t* read = pool + pd.read_woff;
         const int nq = pd.rlen > KMER ? (pd.rlen - KMER + 3) / 4 : 0;   // i = 0,4,.. < rlen-K
@@ -739,7 +743,7 @@ k_dp(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs,
 }
 
 __device__ __forceinline__ void warp_walk_back(const uint32_t* trace, uint32_t* __restrict__ path,
-                                               const int D, int k, const int lane);
+                                               const int D, const int k_end, const int lane, int* stage);
 
 }  // namespace fcx
 
@@ -803,28 +807,39 @@ __global__ void k_tb_scatter(const PairAln* __restrict__ aln, uint32_t n_pairs, 
 
 // Backward walk of one pair by a whole warp (DW_banded.c:264-277): bit d of path[] = "step d came
 // from k+1" (a target-only column).  Lane l holds the record of step 32w + l, so one coalesced
-// request brings 32 records (1 KB); the 32 dependent steps then run on shuffles.  Called by the DP
-// warp right after the forward pass of an accepted pair (k_dp3), or by k_traceback_walk for the
-// round-1 DP kernels.
+// request brings 32 records (1 KB).  The walk is a chain over the CELL INDEX idx = (k - min_k) / 2:
+//        up = bit idx of the step's ballot words;   idx' = idx + a + up,
+// with a = (min_k(d) - min_k(d-1) - 1) / 2 known per record before the chain starts, so that a step
+// of the chain is select / shift / and / add; the per-step operands (w0, w1, a) are staged in 512
+// bytes of shared memory and read back as one broadcast LDS.128 per step.
+// Called by the DP warp right after the forward pass of an accepted pair (k_dp3), or by
+// k_traceback_walk for the round-1 DP kernels.  stage: 128 ints of shared memory owned by the warp.
 __device__ __forceinline__ void warp_walk_back(const uint32_t* trace, uint32_t* __restrict__ path,
-                                               const int D, int k, const int lane) {
+                                               const int D, const int k_end, const int lane, int* stage) {
+    int idx = 0;
     for (int w = D >> 5; w >= 0; w--) {
         const int d_l = 32 * w + lane;
-        uint32_t mk = 0, w0 = 0, w1 = 0;
+        int4 mine = make_int4(0, 0, 0, 0);                 // w0, w1, a, min_k: a no-op step
         if (d_l >= 1 && d_l <= D) {
             const uint32_t* rec = trace + (size_t)d_l * TRACE_REC_WORDS;
             const uint2 hd = *reinterpret_cast<const uint2*>(rec);
-            mk = hd.x; w0 = hd.y; w1 = rec[2];
+            const int mk_prev = (int)rec[-TRACE_REC_WORDS];
+            mine = make_int4((int)hd.y, (int)rec[2], ((int)hd.x - mk_prev - 1) >> 1, (int)hd.x);
         }
+        __syncwarp();
+        reinterpret_cast<int4*>(stage)[lane] = mine;
+        __syncwarp();
+        if (w == (D >> 5)) idx = (k_end - reinterpret_cast<const int4*>(stage)[D & 31].w) >> 1;
         uint32_t acc = 0;
-        const int l_hi = min(31, D - 32 * w), l_lo = w == 0 ? 1 : 0;
-        for (int l = l_hi; l >= l_lo; l--) {
-            const int idx = (k - (int)__shfl_sync(FULL, mk, l)) >> 1;
-            uint32_t word = __shfl_sync(FULL, idx < 32 ? w0 : w1, l);
-            if (idx >= 64) word = trace[(size_t)(32 * w + l) * TRACE_REC_WORDS + 1 + (idx >> 5)];   // wide bands: rare
+#pragma unroll
+        for (int l = 31; l >= 0; l--) {
+            const int4 st = reinterpret_cast<const int4*>(stage)[l];
+            uint32_t word = (uint32_t)(idx < 32 ? st.x : st.y);
+            if (idx >= 64 && 32 * w + l >= 1 && 32 * w + l <= D)                  // wide bands: rare
+                word = trace[(size_t)(32 * w + l) * TRACE_REC_WORDS + 1 + (idx >> 5)];
             const uint32_t up = (word >> (idx & 31)) & 1u;
             acc |= up << l;
-            k += up ? 1 : -1;
+            idx += st.z + (int)up;
         }
         if (lane == 0) path[w] = acc;
     }
@@ -836,13 +851,15 @@ __global__ void __launch_bounds__(128)
 k_traceback_walk(const PairAlloc* __restrict__ allocs, const uint32_t* __restrict__ order,
                  const uint32_t* __restrict__ n_order, const uint32_t* trace_arena,
                  uint32_t* __restrict__ path_arena, const PairAln* __restrict__ aln) {
+    __shared__ int s_stage[4][128];
     const int lane = threadIdx.x & 31;
     const uint32_t n = *n_order;
     for (uint32_t slot = blockIdx.x * 4 + (threadIdx.x >> 5); slot < n; slot += gridDim.x * 4) {
         const uint32_t p = order[slot];
         const PairAlloc al = allocs[p];
         const PairAln a = aln[p];
-        warp_walk_back(trace_arena + al.trace_off * TRACE_REC_WORDS, path_arena + al.path_off, a.dist, a.k_end, lane);
+        warp_walk_back(trace_arena + al.trace_off * TRACE_REC_WORDS, path_arena + al.path_off, a.dist, a.k_end, lane,
+                       s_stage[threadIdx.x >> 5]);
     }
 }
 

@@ -27,7 +27,7 @@
 namespace fcx {
 
 // info = (coverage > min_cov) << 31 | t_pos << 3 | base
-struct CnsRec { int32_t pred; int32_t info; int32_t score2; };
+struct CnsRec { int32_t pred; int32_t info; int32_t score2; int32_t pad; };   // 16 bytes: one vector store / load
 struct CnsOut { int32_t len; int32_t err; int32_t start; int32_t positions; };
 
 // link key: delta << 16 | base << 13 | pred  with  pred = pred_delta << 3 | pred_base, or 0x1fff for
@@ -141,15 +141,18 @@ k_vote(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, uint32_t n_tiles
 
 // ------------------------------------------------------------------------------ k_cns_dp
 // One WARP per seed block, lanes parallel over the LINKS of the current position.  The chain over
-// positions is inherent (falcon.c:405-475), so what matters is the latency of one link of the chain:
+// positions is inherent (falcon.c:405-475), so what matters is the latency and the instruction
+// count of one link of the chain:
 //   * the position slots do not depend on the chain: they are streamed three loads (six positions)
 //     ahead through registers, 256 coalesced bytes = two positions per load;
-//   * the column scores / record ids of the previous and the current position sit in shared memory
-//     (delta levels < CDP_SL; deeper levels, which need an insertion run of >= CDP_SL bases, fall
-//     back to a per-block global table);
-//   * lane e scores link e; the best link of each of the (<= 5) columns of a delta level is a
-//     warp max-reduction, ties resolved towards the lowest lane = first appearance (the slot keeps
-//     links in first-appearance order inside a level);
+//   * the column (score, record id) pairs of the previous and the current position sit in shared
+//     memory (delta levels < CDP_SL; deeper levels, which need an insertion run of >= CDP_SL bases,
+//     fall back to a per-block global table);
+//   * lane e scores link e; a delta level is closed column by column, LIVE columns only (one
+//     warp OR-reduction gives the set): the best link of a column is a warp max-reduction, ties
+//     resolved towards the lowest lane = first appearance (the slot keeps links in first-appearance
+//     order inside a level);
+//   * positions with more than 32 links (deep, noisy pile-ups) take a chunked slow path;
 //   * the backtrack walks the record list through a shared-memory window (records are appended in
 //     position order, so the predecessor is almost always a few records back).
 constexpr int CDP_WARPS = 4;
@@ -157,15 +160,97 @@ constexpr int CDP_SL = 12;               // delta levels with shared-memory colu
 constexpr int CDP_LEVELS = 256;          // deltas 0..255 (the tag cut at 255 keeps delta <= 254)
 constexpr int CDP_WIN = 256;             // records per backtrack window
 
-__global__ void __launch_bounds__(CDP_WARPS * 32)
+struct CdpState {                        // per-block running state of the DP
+    uint32_t nrec; int g_best2, g_rec, g_ck, err;
+};
+
+__device__ __forceinline__ int2* cdp_tab(int2* s_tab, int2* gtab, const int which, const int idx) {
+    return idx < CDP_SL * 5 ? s_tab + which * (CDP_SL * 5) + idx : gtab + which * (CDP_LEVELS * 5) + idx;
+}
+
+// Close column (lev, k) of position i: record, column table, global best (falcon.c:420-469).
+// All arguments are warp-uniform; lane 0 stores.
+__device__ __forceinline__ void cdp_close_column(CdpState& S, const int lane, const int i, const int lev, const int k,
+                                                 int col_sc2, int col_pred, int best_ck, const int hi_flag,
+                                                 const uint32_t rec_cap, CnsRec* __restrict__ recs,
+                                                 int2* s_tab, int2* gtab, const int cur) {
+    if (col_sc2 <= -2) { col_sc2 = -2; col_pred = 0; best_ck = -1; }               // floored (falcon.c:447)
+    uint32_t ridx;
+    if (i == 0 && lev == 0 && k == 0) ridx = 0; else { ridx = S.nrec; S.nrec++; }
+    if (ridx >= rec_cap) { S.err = 2; ridx = rec_cap - 1; }
+    if (lane == 0) {
+        *reinterpret_cast<int4*>(recs + ridx) = make_int4(col_pred, hi_flag | (i << 3) | k, col_sc2, 0);
+        *cdp_tab(s_tab, gtab, cur, lev * 5 + k) = make_int2(col_sc2, (int)ridx);
+    }
+    if (col_sc2 > S.g_best2) { S.g_best2 = col_sc2; S.g_rec = (int)ridx; S.g_ck = best_ck; }
+}
+
+// A position with more than 32 links: chunks of 32 links, the per-column state of the open level
+// carried across chunks.
+__device__ FCX_NOINLINE void cdp_position_slow(CdpState& S, const int lane, const int i, const int n, const int coverage,
+                                               const int hi_flag, const uint2* __restrict__ slot, const uint2* __restrict__ ovf,
+                                               const uint32_t rec_cap, CnsRec* __restrict__ recs, int2* s_tab, int2* gtab,
+                                               const int cur) {
+    int best[5], bpred[5], bck[5], nl[5];
+    int lev = -1;
+#ifdef FCX_EMU
+    if (lane == 0 && getenv("FCX_EMU_TRACE_WIDE")) fprintf(stderr, "k_cns_dp: position %d has %d links (chunked path)\n", i, n);
+#endif
+    auto close_level = [&]() {
+#pragma unroll
+        for (int k = 0; k < 5; k++)
+            if (nl[k] != 0) cdp_close_column(S, lane, i, lev, k, best[k], bpred[k], bck[k], hi_flag, rec_cap, recs, s_tab, gtab, cur);
+        __syncwarp();
+    };
+    for (int e0 = 0; e0 < n; e0 += 32) {
+        const int e = e0 + lane;
+        const bool valid = e < n;
+        uint2 lk = make_uint2(0u, 0u);
+        if (valid) lk = e < VSLOT - 1 ? slot[1 + e] : ovf[e - (VSLOT - 1)];
+        const int lev_e = valid ? (int)(lk.x >> 16) : INT_MAX;
+        const int kk = (int)((lk.x >> 13) & 7u);
+        const uint32_t pred = lk.x & 0x1fffu;
+        const int lev_lo = __shfl_sync(FULL, lev_e, 0), lev_hi = __shfl_sync(FULL, lev_e, min(32, n - e0) - 1);
+        for (int L = lev_lo; L <= lev_hi; L++) {
+            if (L != lev) {
+                if (lev >= 0) close_level();
+                lev = L;
+#pragma unroll
+                for (int k = 0; k < 5; k++) { best[k] = INT_MIN; bpred[k] = -1; bck[k] = 0; nl[k] = 0; }
+            }
+            const bool mine = valid && lev_e == L;
+            int s2 = 2 * (int)lk.y - coverage, prj = -1;
+            if (mine && pred != LK_START) {
+                const int2 v = *cdp_tab(s_tab, gtab, L == 0 ? (cur ^ 1) : cur, (int)(pred >> 3) * 5 + (int)(pred & 7u));
+                s2 += v.x; prj = v.y;
+            }
+#pragma unroll
+            for (int k = 0; k < 5; k++) {
+                const bool in_col = mine && kk == k;
+                const unsigned m = __ballot_sync(FULL, in_col);
+                if (m == 0u) continue;
+                const int cand = in_col ? s2 : INT_MIN;
+                const int cb = __reduce_max_sync(FULL, cand);
+                if (nl[k] == 0 || cb > best[k]) {                 // strict '>': the first link wins ties
+                    const int wl = __ffs(__ballot_sync(FULL, in_col && cand == cb)) - 1;
+                    best[k] = cb; bpred[k] = __shfl_sync(FULL, prj, wl);
+                    bck[k] = nl[k] + __popc(m & ((1u << wl) - 1u));
+                }
+                nl[k] += __popc(m);
+            }
+        }
+    }
+    if (lev >= 0) close_level();
+}
+
+__global__ void __launch_bounds__(CDP_WARPS * 32, 5)
 k_cns_dp(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, const VoteMeta* __restrict__ vmeta,
          const uint2* __restrict__ slot_arena, const uint2* __restrict__ ovf_arena,
          CnsRec* __restrict__ rec_arena, int32_t* __restrict__ lvl_scratch,
          char* __restrict__ cns_arena, int32_t* __restrict__ eqv_arena, int want_eqv, unsigned min_cov,
          CnsOut* __restrict__ out) {
-    __shared__ int32_t s_sc[CDP_WARPS][2][CDP_SL * 5];
-    __shared__ int32_t s_rc[CDP_WARPS][2][CDP_SL * 5];
-    __shared__ int32_t s_win[CDP_WARPS][CDP_WIN * 3];
+    __shared__ int2 s_tabs[CDP_WARPS][2 * CDP_SL * 5];
+    __shared__ int4 s_win[CDP_WARPS][CDP_WIN];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t b = blockIdx.x * CDP_WARPS + wib;
     if (b >= n_blocks) return;                    // (no CTA-wide barrier below)
@@ -188,21 +273,14 @@ k_cns_dp(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, const VoteMeta
     i_hi = min(i_hi, t_len);
     co.positions = i_hi - i_lo;
 
-    // column scores / record ids of the previous and the current position, indexed delta * 5 + base
-    int32_t* gtab = lvl_scratch + (size_t)b * (4 * CDP_LEVELS * 5);
-    auto SC = [&](const int which, const int idx) -> int32_t* {
-        return idx < CDP_SL * 5 ? &s_sc[wib][which][idx] : gtab + which * (CDP_LEVELS * 5) + idx;
-    };
-    auto RC = [&](const int which, const int idx) -> int32_t* {
-        return idx < CDP_SL * 5 ? &s_rc[wib][which][idx] : gtab + (2 + which) * (CDP_LEVELS * 5) + idx;
-    };
+    // column (score, record id) of the previous and the current position, indexed delta * 5 + base
+    int2* s_tab = s_tabs[wib];
+    int2* gtab = reinterpret_cast<int2*>(lvl_scratch + (size_t)b * (4 * CDP_LEVELS * 5));
     int cur = 0;
 
     // record 0 is reserved for column (0,0,'A'): the target of floored columns' best_p = (0,0,0)
-    if (lane == 0) { recs[0].pred = 0; recs[0].info = 0; recs[0].score2 = -2; }
-    uint32_t nrec = 1;
-    int g_best2 = -2, g_rec = -1, g_ck = 0;
-    int err = 0;
+    if (lane == 0) *reinterpret_cast<int4*>(recs) = make_int4(0, 0, -2, 0);
+    CdpState S; S.nrec = 1; S.g_best2 = -2; S.g_rec = -1; S.g_ck = 0; S.err = 0;
     const uint2* slots = slot_arena + bd.slot_off * VSLOT;
     // two positions (32 uint2 = 256 bytes) per load: lanes 0-15 position i0, lanes 16-31 position i0 + 1
     auto load2 = [&](const int i0) -> uint2 {
@@ -218,109 +296,81 @@ k_cns_dp(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, const VoteMeta
         const int i = i0 + half;
         if (i >= i_hi) break;
         const int basel = half * 16;
-        const uint32_t hx = __shfl_sync(FULL, v.x, basel), hy = __shfl_sync(FULL, v.y, basel);
+        const uint32_t hx = __shfl_sync(FULL, v.x, basel);
         const int n = (int)(hx >> 16), coverage = (int)(hx & 0xffffu);
         const int hi_flag = ((unsigned)coverage > min_cov) ? (int)0x80000000 : 0;
         if (i == 0 && lane == 0) recs[0].info = hi_flag;
-        // links 0..14 of the position sit in the slot; lane e < 15 takes link e
-        const uint32_t sx = __shfl_sync(FULL, v.x, (basel + 1 + lane) & 31), sy = __shfl_sync(FULL, v.y, (basel + 1 + lane) & 31);
         if (coverage == 0) { cur ^= 1; continue; }
-        const uint2* ovf = ovf_arena + hy;
-
-        int best[5], bpred[5], bck[5], nl[5];
-        int lev = -1;                          // the open delta level
-        // ---- close a level in base order: records, column scores, global best (falcon.c:420-469)
-        auto close_level = [&]() {
-#pragma unroll
-            for (int k = 0; k < 5; k++) {
-                if (nl[k] == 0) continue;      // dead column: never referenced (a link's predecessor column
-                                               // always carries the previous tag of the same read)
-                int col_sc2 = best[k], col_pred = bpred[k], best_ck = bck[k];
-                if (col_sc2 <= -2) { col_sc2 = -2; col_pred = 0; best_ck = -1; }               // floored (falcon.c:447)
-                uint32_t ridx;
-                if (i == 0 && lev == 0 && k == 0) ridx = 0; else { ridx = nrec; nrec++; }
-                if (ridx >= bd.rec_cap) { err = 2; ridx = bd.rec_cap - 1; }
-                if (lane == 0) {
-                    recs[ridx].pred = col_pred; recs[ridx].info = hi_flag | (i << 3) | k; recs[ridx].score2 = col_sc2;
-                    *SC(cur, lev * 5 + k) = col_sc2; *RC(cur, lev * 5 + k) = (int32_t)ridx;
-                }
-                if (col_sc2 > g_best2) { g_best2 = col_sc2; g_rec = (int)ridx; g_ck = best_ck; }
-            }
-            __syncwarp();                      // the next level (or position) reads these columns
-        };
-        for (int e0 = 0; e0 < n; e0 += 32) {
-            const int e = e0 + lane;
-            const bool valid = e < n;
-            uint32_t kx = sx, ky = sy;
-            if (valid && e >= VSLOT - 1) { const uint2 o = ovf[e - (VSLOT - 1)]; kx = o.x; ky = o.y; }
-            const int lev_e = valid ? (int)(kx >> 16) : INT_MAX;
-            const int kk = (int)((kx >> 13) & 7u);
-            const uint32_t pred = kx & 0x1fffu;
-            const int lev_lo = __shfl_sync(FULL, lev_e, 0), lev_hi = __shfl_sync(FULL, lev_e, min(32, n - e0) - 1);
-            // links are sorted by level and levels are contiguous: every delta-d tag follows a
-            // delta-(d-1) tag of the same read
-            for (int L = lev_lo; L <= lev_hi; L++) {
-                if (L != lev) {
-                    if (lev >= 0) close_level();
-                    lev = L;
-#pragma unroll
-                    for (int k = 0; k < 5; k++) { best[k] = INT_MIN; bpred[k] = -1; bck[k] = 0; nl[k] = 0; }
-                }
-                const bool mine = valid && lev_e == L;
-                int s2 = 2 * (int)ky - coverage, prj = -1;
-                if (mine && pred != LK_START) {
-                    const int slotp = (int)(pred >> 3) * 5 + (int)(pred & 7u);
-                    const int which = L == 0 ? (cur ^ 1) : cur;       // predecessor columns: position i-1 for delta 0
-                    s2 += *SC(which, slotp); prj = *RC(which, slotp);
-                }
-#pragma unroll
-                for (int k = 0; k < 5; k++) {
-                    const bool in_col = mine && kk == k;
-                    const unsigned m = __ballot_sync(FULL, in_col);
-                    if (m == 0u) continue;
-                    const int cand = in_col ? s2 : INT_MIN;
-                    const int cb = __reduce_max_sync(FULL, cand);
-                    if (nl[k] == 0 || cb > best[k]) {                 // strict '>': the first link wins ties
-                        const int wl = __ffs(__ballot_sync(FULL, in_col && cand == cb)) - 1;
-                        best[k] = cb; bpred[k] = __shfl_sync(FULL, prj, wl);
-                        bck[k] = nl[k] + __popc(m & ((1u << wl) - 1u));
-                    }
-                    nl[k] += __popc(m);
-                }
-            }
+        if (n > 32) {
+            const uint32_t hy = __shfl_sync(FULL, v.y, basel);
+            cdp_position_slow(S, lane, i, n, coverage, hi_flag, slots + (size_t)i * VSLOT, ovf_arena + hy, bd.rec_cap, recs,
+                              s_tab, gtab, cur);
+            cur ^= 1;
+            continue;
         }
-        if (lev >= 0) close_level();
+        // links 0..14 of the position sit in the slot; lane e takes link e
+        uint32_t kx = __shfl_sync(FULL, v.x, (basel + 1 + lane) & 31), ky = __shfl_sync(FULL, v.y, (basel + 1 + lane) & 31);
+        if (n > VSLOT - 1) {
+            const uint32_t hy = __shfl_sync(FULL, v.y, basel);
+            if (lane >= VSLOT - 1 && lane < n) { const uint2 o = ovf_arena[hy + (uint32_t)(lane - (VSLOT - 1))]; kx = o.x; ky = o.y; }
+        }
+        const int lev_e = lane < n ? (int)(kx >> 16) : -1;
+        const int kk = (int)((kx >> 13) & 7u);
+        const uint32_t pred = kx & 0x1fffu;
+        const int slotp = (int)(pred >> 3) * 5 + (int)(pred & 7u);
+        const int base2 = 2 * (int)ky - coverage;
+        const int maxlev = __shfl_sync(FULL, lev_e, n - 1);
+        // levels are contiguous: every delta-d tag follows a delta-(d-1) tag of the same read
+        for (int L = 0; L <= maxlev; L++) {
+            const bool mine = lev_e == L;
+            int s2 = base2, prj = -1;
+            if (mine && pred != LK_START) {
+                const int2 pv = *cdp_tab(s_tab, gtab, L == 0 ? (cur ^ 1) : cur, slotp);    // predecessor columns: position i-1 for delta 0
+                s2 += pv.x; prj = pv.y;
+            }
+            unsigned cols = __reduce_or_sync(FULL, mine ? (1u << kk) : 0u);
+            while (cols) {                                        // live columns in base order
+                const int k = __ffs(cols) - 1;
+                cols &= cols - 1u;
+                const bool in_col = mine && kk == k;
+                const int cand = in_col ? s2 : INT_MIN;
+                const int cb = __reduce_max_sync(FULL, cand);
+                const unsigned colmask = __ballot_sync(FULL, in_col);
+                const int wl = __ffs(__ballot_sync(FULL, in_col && cand == cb)) - 1;      // first link wins ties
+                cdp_close_column(S, lane, i, L, k, cb, __shfl_sync(FULL, prj, wl), __popc(colmask & ((1u << wl) - 1u)),
+                                 hi_flag, bd.rec_cap, recs, s_tab, gtab, cur);
+            }
+            __syncwarp();                                         // the next level (or position) reads these columns
+        }
         cur ^= 1;
       }
     }
     // ------------------------------------------------------------ backtrack (falcon.c:479-542)
     // The string is produced back to front; it is written from the END of the block's output area
     // towards lower addresses, so no reversal is needed: the consensus starts at cns[start].
-    if (g_rec < 0) err = 3;                       // reference: assert(g_best_score != -1)
+    int err = S.err;
+    if (S.g_rec < 0) err = 3;                     // reference: assert(g_best_score != -1)
     const int cap = 2 * t_len + 4;
     int pos = cap;                                // one past the last byte written so far
     if (err == 0) {
-        int32_t* win = s_win[wib];
+        int4* win = s_win[wib];
         int wlo = 0, whi = -1;                    // the window holds records wlo..whi
-        auto fetch = [&](const int r, int& r_pred, int& r_info, int& r_sc) {
+        auto fetch = [&](const int r) -> int4 {
             if (r < wlo || r > whi) {
                 __syncwarp();
                 whi = r; wlo = max(0, r - (CDP_WIN - 1));
-                const int32_t* src = reinterpret_cast<const int32_t*>(recs + wlo);
-                const int nw = (whi - wlo + 1) * 3;
-                for (int j = lane; j < nw; j += 32) win[j] = src[j];
+                const int4* src = reinterpret_cast<const int4*>(recs + wlo);
+                for (int j = lane; j <= whi - wlo; j += 32) win[j] = src[j];
                 __syncwarp();
             }
-            const int o = (r - wlo) * 3;
-            r_pred = win[o]; r_info = win[o + 1]; r_sc = win[o + 2];
+            return win[r - wlo];
         };
         __syncwarp();                             // lane 0's record stores are visible to every lane
-        char bb = '$'; int ck = g_ck;
+        char bb = '$'; int ck = S.g_ck;
         unsigned index = 0; const unsigned lim = (unsigned)t_len * 2u;
-        int r_pred, r_info, r_sc;
-        fetch(g_rec, r_pred, r_info, r_sc);
+        int4 r = fetch(S.g_rec);                  // x pred, y info, z score2
         for (;;) {
-            const bool hi = r_info < 0;
+            const bool hi = r.y < 0;
             switch (ck) {
                 case 0: bb = hi ? 'A' : 'a'; break;
                 case 1: bb = hi ? 'C' : 'c'; break;
@@ -329,16 +379,15 @@ k_cns_dp(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, const VoteMeta
                 case 4: bb = '-'; break;
                 default: break;
             }
-            if (r_pred == -1 || index >= lim) break;
-            int p_pred, p_info, p_sc;
-            fetch(r_pred, p_pred, p_info, p_sc);
+            if (r.x == -1 || index >= lim) break;
+            const int4 pr = fetch(r.x);
             if (bb != '-') {
                 pos--;
-                if (lane == 0) { cns[pos] = bb; if (want_eqv) eqv[pos] = r_sc / 2 - p_sc / 2; }
+                if (lane == 0) { cns[pos] = bb; if (want_eqv) eqv[pos] = r.z / 2 - pr.z / 2; }
                 index++;
             }
-            ck = p_info & 7;
-            r_pred = p_pred; r_info = p_info; r_sc = p_sc;
+            ck = pr.y & 7;
+            r = pr;
         }
         if (lane == 0) cns[cap] = 0;
     }

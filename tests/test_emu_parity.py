@@ -201,3 +201,16 @@ def test_device_trim_vs_reference(emu, ref):
     G._check_trim(emu, ref, synth.make_set(30000, 3000, 14, seed=21, n_blocks=3))
     G._check_trim(emu, ref, synth.make_set(30000, 2500, 20, seed=23, n_blocks=2, len_sigma=0.4), edge_tolerance=500,
                   trim_size=80, max_n_read=6, max_cov_aln=2)
+
+
+def test_deep_noisy_pileup_takes_the_chunked_consensus_path(emu, oracle):
+    """> 32 distinct links at one seed position (deep coverage, high insertion rate): k_cns_dp's
+    chunked slow path and the vote overflow arena."""
+    rng = np.random.default_rng(5)
+    g = synth.random_codes(700, rng)
+    seed = synth.codes_to_bytes(g)
+    reads = [synth.codes_to_bytes(synth.add_errors(g, rng, 0.13, 0.11, 0.01)) for _ in range(1500)]   # 6 positions with > 32 links
+    seqs = [seed, seed] + reads
+    emu.upload_pool(seqs)
+    got = emu.consensus_blocks([list(range(len(seqs)))], 4, 0.60)[0]
+    assert got == oracle.generate_consensus(seqs, 4, 0.60)
