@@ -334,7 +334,8 @@ def main():
         eng.pool_commit()
 
     def run_blocks():
-        return eng.consensus_blocks_raw(block_off, ids, args.min_cov, args.min_idt)
+        # views of the engine's result buffers (host memory): the step's output, no extra Python copy
+        return eng.consensus_blocks_raw(block_off, ids, args.min_cov, args.min_idt, copy=False)
 
     def gather_to_rank0(data, off):
         """Consensus bytes + lengths of every rank -> rank 0, merged in seed order."""
@@ -376,7 +377,7 @@ def main():
 
     # ---------------------------------------------------------------- resident-store path
     build_store()
-    first = run_blocks()
+    first = tuple(a.copy() for a in run_blocks())
     for _ in range(max(0, args.warmup - 1)):
         run_blocks()
     sampler = ClockSampler(local_rank)
@@ -404,6 +405,7 @@ def main():
             d, o = run_blocks()
             return gather_to_rank0(d, o)
         merged = step_e2e()
+        merged = tuple(a.copy() for a in merged) if merged[0] is not None else merged
         for _ in range(max(0, args.warmup - 1)):
             step_e2e()
         _, e_wall = timed(step_e2e, args.steps)

@@ -263,7 +263,9 @@ class Engine:
 
     # -- consensus ----------------------------------------------------------------------
     def consensus_blocks_raw(self, block_off: np.ndarray, read_ids: np.ndarray, min_cov: int,
-                             min_idt: float, K: int = 8) -> Tuple[np.ndarray, np.ndarray]:
+                             min_idt: float, K: int = 8, copy: bool = True) -> Tuple[np.ndarray, np.ndarray]:
+        """-> (consensus bytes of all blocks back to back, n_blocks + 1 offsets).  With copy=False the
+        arrays are views of the engine's own result buffers (host memory), valid until the next call."""
         block_off = np.ascontiguousarray(block_off, dtype=np.uint32)
         read_ids = np.ascontiguousarray(read_ids, dtype=np.uint32)
         nb = block_off.shape[0] - 1
@@ -272,13 +274,13 @@ class Engine:
                                                    read_ids.ctypes.data, min_cov, K, min_idt,
                                                    C.byref(ob), C.byref(oo)),
                     "fcx_consensus_blocks")
-        off = np.ctypeslib.as_array((C.c_uint64 * (nb + 1)).from_address(oo.value)).copy()
+        off = np.ctypeslib.as_array((C.c_uint64 * (nb + 1)).from_address(oo.value))
         total = int(off[-1])
         if total:
-            data = np.ctypeslib.as_array((C.c_uint8 * total).from_address(ob.value)).copy()
+            data = np.ctypeslib.as_array((C.c_uint8 * total).from_address(ob.value))
         else:
             data = np.zeros(0, dtype=np.uint8)
-        return data, off
+        return (data.copy(), off.copy()) if copy else (data, off)
 
     def consensus_blocks(self, blocks: Sequence[Sequence[int]], min_cov: int, min_idt: float,
                          K: int = 8) -> List[bytes]:
@@ -385,7 +387,7 @@ class MultiEngine(Engine):
         return int(self._lib.fcx_multi_peer_bytes(self._h))
 
     def consensus_blocks_raw(self, block_off: np.ndarray, read_ids: np.ndarray, min_cov: int,
-                             min_idt: float, K: int = 8) -> Tuple[np.ndarray, np.ndarray]:
+                             min_idt: float, K: int = 8, copy: bool = True) -> Tuple[np.ndarray, np.ndarray]:
         block_off = np.ascontiguousarray(block_off, dtype=np.uint32)
         read_ids = np.ascontiguousarray(read_ids, dtype=np.uint32)
         nb = block_off.shape[0] - 1
@@ -393,10 +395,10 @@ class MultiEngine(Engine):
         self._check(self._lib.fcx_multi_consensus_blocks(self._h, nb, block_off.ctypes.data, read_ids.ctypes.data,
                                                          min_cov, K, min_idt, C.byref(ob), C.byref(oo)),
                     "fcx_multi_consensus_blocks")
-        off = np.ctypeslib.as_array((C.c_uint64 * (nb + 1)).from_address(oo.value)).copy()
+        off = np.ctypeslib.as_array((C.c_uint64 * (nb + 1)).from_address(oo.value))
         total = int(off[-1])
-        data = np.ctypeslib.as_array((C.c_uint8 * total).from_address(ob.value)).copy() if total else np.zeros(0, dtype=np.uint8)
-        return data, off
+        data = np.ctypeslib.as_array((C.c_uint8 * total).from_address(ob.value)) if total else np.zeros(0, dtype=np.uint8)
+        return (data.copy(), off.copy()) if copy else (data, off)
 
     def pair_info(self) -> List[PairInfo]:
         n = C.c_uint64()

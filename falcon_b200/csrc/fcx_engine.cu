@@ -13,11 +13,13 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <climits>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -355,9 +357,16 @@ namespace {
 
 inline uint64_t max_d_of(int q_len, int t_len) { return (uint64_t)(int)(0.3 * (q_len + t_len)); }
 
+double now_ms() {
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
 int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* block_off, const uint32_t* read_ids,
              unsigned min_cov, double min_idt, WaveResult& res) {
     const uint32_t nb = b1 - b0;
+    static const bool trace_waves = getenv("FCX_TRACE_WAVES") != nullptr;
+    double tl[8] = {0}; tl[0] = now_ms();
     if (ctx->debug_split_above && nb > ctx->debug_split_above) { L.err = "out of device memory (simulated)"; return 100; }
     std::vector<BlockDesc> hb(nb);
     uint64_t npairs64 = 0, kpos_total = 0, rec_total = 0, cns_total = 0, slot_total = 0, tiles = 0;
@@ -426,6 +435,7 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
     if (np) CKL(cudaMemcpyAsync(L.d_pairs.p, hp.data(), (size_t)np * sizeof(PairDesc), cudaMemcpyHostToDevice, st));
     const uint32_t* pool = ctx->d_pool.as<uint32_t>();
 
+    tl[1] = now_ms();
     // ---- index
     CKL(cudaEventRecord(L.ev[0], st));
     CKL(cudaMemsetAsync(L.d_ktab.p, 0, (size_t)nb * KTAB * 4, st));
@@ -457,7 +467,9 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
         CKL(cudaMemcpyAsync(L.h_ranges.p, L.d_ranges.p, (size_t)np * sizeof(PairRange), cudaMemcpyDeviceToHost, st));
     }
     CKL(cudaEventRecord(L.ev[2], st));
+    tl[2] = now_ms();
     CKL(cudaStreamSynchronize(st));
+    tl[3] = now_ms();
     // ---- exact per-pair allocations
     std::vector<PairAlloc> ha(np);
     uint64_t trace_recs = 0, xam_n = 0, xck_n = 0, path_w = 0, dp_pairs = 0, span_bases = 0; uint32_t max_span = 0;
@@ -484,6 +496,7 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
     CKR(L.d_ent.reserve(xam_n * 4 + 128));
     CKR(L.d_path.reserve(path_w * 4 + 64));
     if (np) CKL(cudaMemcpyAsync(L.d_allocs.p, ha.data(), (size_t)np * sizeof(PairAlloc), cudaMemcpyHostToDevice, st));
+    tl[4] = now_ms();
     // ---- DP
     CKL(cudaEventRecord(L.ev[3], st));
     if (np) {
@@ -581,7 +594,9 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
     }
     int vote_err = 0;
     CKL(cudaMemcpyAsync(&vote_err, L.d_counter.as<int>() + 5, 4, cudaMemcpyDeviceToHost, sh));
+    tl[5] = now_ms();
     CKL(cudaStreamSynchronize(sh));
+    tl[6] = now_ms();
     if (vote_err) {
         L.err = vote_err == 1 ? "consensus vote: more than 160 distinct links at one seed position"
                               : "consensus vote: link overflow arena exhausted";
@@ -631,6 +646,11 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
     L.counters[FCX_C_ACCEPTED] += accepted; L.counters[FCX_C_TRACE_CELLS] += cells;
     L.counters[FCX_C_DP_STEPS] += steps; L.counters[FCX_C_ALN_COLS] += cols;
     L.counters[FCX_C_SPAN_BASES] += span_bases; L.counters[FCX_C_WAVES] += 1;
+    tl[7] = now_ms();
+    if (trace_waves)
+        fprintf(stderr, "wave lane %d blocks %u..%u pairs %u: t0 %.1f prep %.1f launch1 %.1f wait1 %.1f alloc %.1f launch2 %.1f wait2 %.1f collect %.1f\n",
+                (int)(&L - ctx->lanes.data()), b0, b1, np, tl[0], tl[1] - tl[0], tl[2] - tl[1], tl[3] - tl[2], tl[4] - tl[3],
+                tl[5] - tl[4], tl[6] - tl[5], tl[7] - tl[6]);
     float ms;
     cudaEventElapsedTime(&ms, L.ev[0], L.ev[1]); L.times[FCX_T_INDEX] += ms;
     cudaEventElapsedTime(&ms, L.ev[1], L.ev[2]); L.times[FCX_T_RANGE] += ms;
@@ -728,6 +748,27 @@ extern "C" int fcx_consensus_blocks(fcx_ctx* ctx, uint32_t n_blocks, const uint3
         out.eqv = std::move(a.eqv); out.eqv.insert(out.eqv.end(), b.eqv.begin(), b.eqv.end());
         return 0;
     };
+    // results are appended to the call's output in block order by whichever lane thread completes
+    // the next wave in line, while the other lanes keep the GPU busy: only the last wave's copy is serial
+    {
+        uint64_t upper = 0;
+        for (uint32_t b = 0; b < n_blocks; b++) upper += (uint64_t)ctx->h_len[read_ids[block_off[b]]] * 2 + 8;
+        ctx->out_bases.reserve(upper); ctx->out_off.reserve((size_t)n_blocks + 1);
+    }
+    std::mutex flush_mtx;
+    std::vector<char> done(waves.size(), 0);
+    size_t flushed = 0;
+    auto flush_ready = [&]() {                       // caller holds flush_mtx
+        while (flushed < waves.size() && done[flushed]) {
+            WaveResult& r = results[flushed];
+            ctx->out_bases.insert(ctx->out_bases.end(), r.bases.begin(), r.bases.end());
+            for (uint64_t l : r.lens) ctx->out_off.push_back(ctx->out_off.back() + l);
+            if (ctx->keep_pair_info) ctx->pair_info.insert(ctx->pair_info.end(), r.info.begin(), r.info.end());
+            if (ctx->want_eqv) ctx->out_eqv.insert(ctx->out_eqv.end(), r.eqv.begin(), r.eqv.end());
+            r = WaveResult();
+            flushed++;
+        }
+    };
     auto worker = [&](int li) {
         cudaSetDevice(ctx->device);
         Lane& L = ctx->lanes[li];
@@ -736,6 +777,9 @@ extern "C" int fcx_consensus_blocks(fcx_ctx* ctx, uint32_t n_blocks, const uint3
             if (w >= waves.size() || failed.load()) break;
             int rc = run_split(L, waves[w].first, waves[w].second, results[w]);
             if (rc) { failed.store(rc); break; }
+            std::lock_guard<std::mutex> g(flush_mtx);
+            done[w] = 1;
+            flush_ready();
         }
     };
     const int nthreads = (int)std::min<size_t>(waves.size(), (size_t)nl);
@@ -748,16 +792,6 @@ extern "C" int fcx_consensus_blocks(fcx_ctx* ctx, uint32_t n_blocks, const uint3
     if (failed.load()) {
         for (auto& L : ctx->lanes) if (!L.err.empty()) { ctx->err = L.err; break; }
         return failed.load();
-    }
-    // ---- merge in block order
-    uint64_t total = 0;
-    for (auto& r : results) total += r.bases.size();
-    ctx->out_bases.reserve(total); ctx->out_off.reserve((size_t)n_blocks + 1);
-    for (auto& r : results) {
-        ctx->out_bases.insert(ctx->out_bases.end(), r.bases.begin(), r.bases.end());
-        for (uint64_t l : r.lens) ctx->out_off.push_back(ctx->out_off.back() + l);
-        if (ctx->keep_pair_info) ctx->pair_info.insert(ctx->pair_info.end(), r.info.begin(), r.info.end());
-        if (ctx->want_eqv) ctx->out_eqv.insert(ctx->out_eqv.end(), r.eqv.begin(), r.eqv.end());
     }
     for (auto& L : ctx->lanes) {
         for (int i = 0; i < FCX_T_COUNT; i++) ctx->times[i] += L.times[i];

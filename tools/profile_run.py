@@ -32,11 +32,14 @@ def main():
     eng = Engine(0)
     eng.set_option("pair_info", 0)
     eng.upload_pool(S.pool)
-    blocks = [b.tolist() for b in S.blocks]
+    import numpy as np
+    boff = np.zeros(len(S.blocks) + 1, dtype=np.uint32)
+    np.cumsum([len(b) for b in S.blocks], out=boff[1:])
+    bids = np.concatenate(S.blocks).astype(np.uint32)
     L = lib()
     for r in range(a.reps):
         t0 = time.time()
-        eng.consensus_blocks(blocks, 4, 0.70)
+        eng.consensus_blocks_raw(boff, bids, 4, 0.70, copy=False)
         dt = time.time() - t0
         st = eng.stats()
         print("rep %d wall %.1f ms  pairs/s %.0f  " % (r, dt * 1e3, st["pairs"] / dt) +
