@@ -164,6 +164,10 @@ DWA = kup
 falcon = kup
 
 
+def device_count() -> int:
+    return int(lib().fcx_device_count())
+
+
 class EngineError(RuntimeError):
     pass
 

@@ -116,11 +116,11 @@ struct fcx_ctx {
     uint64_t counters[FCX_C_COUNT] = {0};
     double prof[8] = {0};
     cudaEvent_t tev[2] = {nullptr, nullptr};
-    size_t arena_budget = (size_t)120 << 30;
+    size_t arena_budget = (size_t)160 << 30;
     uint32_t max_wave_blocks = 2960;     // 148 SMs x 20 resident consensus warps (set from the SM count)
     uint32_t max_wave_pairs = 1u << 19;
     uint32_t min_wave_blocks = 384;
-    int n_lanes = 2;
+    int n_lanes = 3;
     int active_lanes = 0;              // 0 = all
     int dp_variant = 3;                // 3: k_dp3 (default); 1: k_dp (round-1 kernel); 2: k_dp with TMA-staged spans
     uint32_t debug_split_above = 0;    // test hook: pretend waves with more blocks than this do not fit
@@ -161,6 +161,11 @@ static thread_local std::string g_create_err;
     } while (0)
 
 extern "C" const char* fcx_version(void) { return "falcon_b200 0.2 sm_100a"; }
+
+extern "C" int fcx_device_count(void) {
+    int n = 0;
+    return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
 
 extern "C" const char* fcx_last_error(const fcx_ctx* ctx) {
     return ctx ? ctx->err.c_str() : g_create_err.c_str();
@@ -207,7 +212,7 @@ extern "C" int fcx_create(int device, fcx_ctx** out) {
     {   // never plan beyond what the device can actually give
         size_t free_b = 0, total_b = 0;
         CKC(cudaMemGetInfo(&free_b, &total_b));
-        if (!getenv("FCX_ARENA_GB")) ctx->arena_budget = std::min(ctx->arena_budget, (size_t)((double)free_b * 0.70));
+        if (!getenv("FCX_ARENA_GB")) ctx->arena_budget = std::min(ctx->arena_budget, (size_t)((double)free_b * 0.85));
     }
     CKC(cudaFuncSetAttribute(k_range, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (KTAB / 32) * 4 + 4 * RANGE_BINS * (int)sizeof(int) + 24 * 1024));
@@ -695,25 +700,37 @@ extern "C" int fcx_consensus_blocks(fcx_ctx* ctx, uint32_t n_blocks, const uint3
     target = std::min(target, ctx->max_wave_blocks);
     const double budget = (double)ctx->arena_budget / nl;
     std::vector<std::pair<uint32_t, uint32_t>> waves;
-    for (uint32_t b = 0; b < n_blocks;) {
-        uint32_t e = b; uint64_t pairs = 0; double bytes = 0;
-        while (e < n_blocks) {
-            uint32_t lo = block_off[e], hi = block_off[e + 1];
-            int slen = ctx->h_len[read_ids[lo]];
-            const double mdiff = std::max(0.0, 1.0 - min_idt);
-            const double capfrac = std::min(0.3, mdiff < 1.999 ? mdiff / (2.0 - mdiff) : 0.3);
-            double bb = (double)KTAB * 4 + (double)slen * (4 + (8 + (hi - lo - 1) / 16) * 16 + 2 * 5 + 16.0 * VSLOT * 1.5) + 4.0 * CDP_LEVELS * 5 * 4;
-            for (uint32_t i = lo + 1; i < hi; i++) {
-                // typical aligned span ~ 0.65 x the shorter sequence (exact sizes follow k_range;
-                // an under-estimate is caught by the out-of-memory split below)
-                const double span = 0.65 * std::min(ctx->h_len[read_ids[i]], slen);
-                bb += capfrac * 2.0 * span * 33.0 + 8.0 * (span + 2) + 128;
+    auto pack = [&](uint32_t tgt) {
+        waves.clear();
+        for (uint32_t b = 0; b < n_blocks;) {
+            uint32_t e = b; uint64_t pairs = 0; double bytes = 0;
+            while (e < n_blocks) {
+                uint32_t lo = block_off[e], hi = block_off[e + 1];
+                int slen = ctx->h_len[read_ids[lo]];
+                const double mdiff = std::max(0.0, 1.0 - min_idt);
+                const double capfrac = std::min(0.3, mdiff < 1.999 ? mdiff / (2.0 - mdiff) : 0.3);
+                double bb = (double)KTAB * 4 + (double)slen * (4 + (8 + (hi - lo - 1) / 16) * 16 + 2 * 5 + 16.0 * VSLOT * 1.5) + 4.0 * CDP_LEVELS * 5 * 4;
+                for (uint32_t i = lo + 1; i < hi; i++) {
+                    // typical aligned span ~ 0.65 x the shorter sequence (exact sizes follow k_range;
+                    // an under-estimate is caught by the out-of-memory split below)
+                    const double span = 0.65 * std::min(ctx->h_len[read_ids[i]], slen);
+                    bb += capfrac * 2.0 * span * 33.0 + 4.0 * (span + 8) + 128;
+                }
+                if (e > b && (bytes + bb > budget || pairs + (hi - lo - 1) > ctx->max_wave_pairs || e - b >= tgt)) break;
+                bytes += bb; pairs += hi - lo - 1; e++;
             }
-            if (e > b && (bytes + bb > budget || pairs + (hi - lo - 1) > ctx->max_wave_pairs || e - b >= target)) break;
-            bytes += bb; pairs += hi - lo - 1; e++;
+            waves.emplace_back(b, e);
+            b = e;
         }
-        waves.emplace_back(b, e);
-        b = e;
+    };
+    pack(target);
+    // The memory budget may have cut the waves shorter than planned, leaving a small tail wave or a
+    // wave count that does not divide among the lanes: repack into equal waves, a multiple of the
+    // lane count (a short wave still pays the full latency of the serial consensus kernel).
+    if (waves.size() > 1) {
+        const uint32_t nw = (uint32_t)(((waves.size() + nl - 1) / nl) * nl);
+        const uint32_t tgt2 = std::max(ctx->min_wave_blocks, (n_blocks + nw - 1) / nw);
+        if (tgt2 < target || waves.size() % nl) pack(std::min(tgt2, target));
     }
     for (auto& L : ctx->lanes) {
         memset(L.times, 0, sizeof L.times); memset(L.counters, 0, sizeof L.counters); memset(L.prof, 0, sizeof L.prof);

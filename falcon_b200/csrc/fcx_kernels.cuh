@@ -830,16 +830,30 @@ __device__ __forceinline__ void warp_walk_back(const uint32_t* trace, uint32_t* 
         reinterpret_cast<int4*>(stage)[lane] = mine;
         __syncwarp();
         if (w == (D >> 5)) idx = (k_end - reinterpret_cast<const int4*>(stage)[D & 31].w) >> 1;
+        const int idx_in = idx;
         uint32_t acc = 0;
+        int idx_max = idx;
 #pragma unroll
         for (int l = 31; l >= 0; l--) {
             const int4 st = reinterpret_cast<const int4*>(stage)[l];
-            uint32_t word = (uint32_t)(idx < 32 ? st.x : st.y);
-            if (idx >= 64 && 32 * w + l >= 1 && 32 * w + l <= D)                  // wide bands: rare
-                word = trace[(size_t)(32 * w + l) * TRACE_REC_WORDS + 1 + (idx >> 5)];
-            const uint32_t up = (word >> (idx & 31)) & 1u;
+            const unsigned long long both = ((unsigned long long)(uint32_t)st.y << 32) | (uint32_t)st.x;
+            const uint32_t up = (uint32_t)(both >> (idx & 63)) & 1u;
             acc |= up << l;
             idx += st.z + (int)up;
+            idx_max = max(idx_max, idx);
+        }
+        if (idx_max >= 64) {                      // a band wider than 64 cells somewhere in this chunk (rare): redo it
+            idx = idx_in; acc = 0;                // with the ballot words beyond the first two read from the record
+            for (int l = 31; l >= 0; l--) {
+                const int d = 32 * w + l;
+                if (d < 1 || d > D) continue;
+                const int4 st = reinterpret_cast<const int4*>(stage)[l];
+                const uint32_t word = idx < 32 ? (uint32_t)st.x : idx < 64 ? (uint32_t)st.y
+                                               : trace[(size_t)d * TRACE_REC_WORDS + 1 + (idx >> 5)];
+                const uint32_t up = (word >> (idx & 31)) & 1u;
+                acc |= up << l;
+                idx += st.z + (int)up;
+            }
         }
         if (lane == 0) path[w] = acc;
     }

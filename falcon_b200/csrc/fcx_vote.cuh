@@ -321,24 +321,38 @@ k_cns_dp(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, const VoteMeta
         const int base2 = 2 * (int)ky - coverage;
         const int maxlev = __shfl_sync(FULL, lev_e, n - 1);
         // levels are contiguous: every delta-d tag follows a delta-(d-1) tag of the same read
+        const int info0 = hi_flag | (i << 3);
         for (int L = 0; L <= maxlev; L++) {
             const bool mine = lev_e == L;
             int s2 = base2, prj = -1;
             if (mine && pred != LK_START) {
-                const int2 pv = *cdp_tab(s_tab, gtab, L == 0 ? (cur ^ 1) : cur, slotp);    // predecessor columns: position i-1 for delta 0
+                const int which = L == 0 ? (cur ^ 1) : cur;                               // predecessor columns: position i-1 for delta 0
+                const int2 pv = slotp < CDP_SL * 5 ? s_tab[which * (CDP_SL * 5) + slotp] : gtab[which * (CDP_LEVELS * 5) + slotp];
                 s2 += pv.x; prj = pv.y;
             }
             unsigned cols = __reduce_or_sync(FULL, mine ? (1u << kk) : 0u);
+            const bool reserved0 = i == 0 && L == 0;                                      // column (0,0,'A') owns record 0
+            int2* const tab_out = L < CDP_SL ? s_tab + cur * (CDP_SL * 5) + L * 5 : gtab + cur * (CDP_LEVELS * 5) + L * 5;
             while (cols) {                                        // live columns in base order
                 const int k = __ffs(cols) - 1;
                 cols &= cols - 1u;
                 const bool in_col = mine && kk == k;
                 const int cand = in_col ? s2 : INT_MIN;
-                const int cb = __reduce_max_sync(FULL, cand);
-                const unsigned colmask = __ballot_sync(FULL, in_col);
-                const int wl = __ffs(__ballot_sync(FULL, in_col && cand == cb)) - 1;      // first link wins ties
-                cdp_close_column(S, lane, i, L, k, cb, __shfl_sync(FULL, prj, wl), __popc(colmask & ((1u << wl) - 1u)),
-                                 hi_flag, bd.rec_cap, recs, s_tab, gtab, cur);
+                const int cb = __reduce_max_sync(FULL, cand);     // strict '>' in link order: the FIRST best link wins
+                const int wl = __ffs(__ballot_sync(FULL, cand == cb)) - 1;               // (lanes outside the column hold INT_MIN < cb)
+                int col_pred = __shfl_sync(FULL, prj, wl), col_sc2 = cb;
+                if (cb <= -2) { col_sc2 = -2; col_pred = 0; }                             // floored (falcon.c:447)
+                uint32_t ridx = S.nrec;
+                if (reserved0 && k == 0) ridx = 0; else S.nrec++;
+                if (ridx >= bd.rec_cap) { S.err = 2; ridx = bd.rec_cap - 1; }
+                if (lane == 0) {
+                    *reinterpret_cast<int4*>(recs + ridx) = make_int4(col_pred, info0 | k, col_sc2, 0);
+                    tab_out[k] = make_int2(col_sc2, (int)ridx);
+                }
+                if (col_sc2 > S.g_best2) {                        // (a floored column never gets here: g_best2 >= -2)
+                    S.g_best2 = col_sc2; S.g_rec = (int)ridx;
+                    S.g_ck = __popc(__ballot_sync(FULL, in_col) & ((1u << wl) - 1u));     // index of the best link in its column
+                }
             }
             __syncwarp();                                         // the next level (or position) reads these columns
         }

@@ -107,6 +107,9 @@ void free_aln_range(aln_range *);
 /* ---------------------------------------------------------------- batched GPU path */
 typedef struct fcx_ctx fcx_ctx;
 
+/* Number of CUDA devices visible to this process (0 if there is none: falcon_b200 has no CPU path). */
+int fcx_device_count(void);
+
 /* Create an engine bound to CUDA device `device` (one engine per process per GPU). */
 int fcx_create(int device, fcx_ctx **out);
 void fcx_destroy(fcx_ctx *);

@@ -323,3 +323,105 @@ def test_device_trim_vs_reference(engine, ref):
     _check_trim(engine, ref, synth.make_set(60000, 5000, 25, seed=21, n_blocks=4))
     _check_trim(engine, ref, synth.make_set(120000, 15000, 20, seed=22, n_blocks=3), edge_tolerance=600, trim_size=120)
     _check_trim(engine, ref, synth.make_set(40000, 3000, 40, seed=23, n_blocks=3, len_sigma=0.4), max_n_read=10, max_cov_aln=3)
+
+
+def test_multi_engine_shards_one_data_set(engine, oracle):
+    """fcx_multi_*: one read store on every device (peer copies), seed blocks sharded, results merged
+    in seed order.  Uses every visible GPU; on a one-GPU box two engines share device 0."""
+    from falcon_b200.binding import MultiEngine, device_count
+    n = device_count()
+    devs = list(range(n)) if n > 1 else [0, 0]
+    S = synth.make_set(80000, 4000, 20, seed=31, n_blocks=9)
+    blocks = [b.tolist() for b in S.blocks]
+    engine.upload_pool(S.pool)
+    single = engine.consensus_blocks(blocks, 4, 0.70)
+    m = MultiEngine(devs)
+    try:
+        m.upload_pool(S.pool)
+        multi = m.consensus_blocks(blocks, 4, 0.70)
+        assert m.peer_bytes() > 0
+        st = m.stats()
+        assert st["pairs"] == S.n_pairs
+    finally:
+        m.close()
+    assert multi == single
+    for bi in (0, len(blocks) - 1):
+        assert multi[bi] == oracle.generate_consensus(S.block_seqs(bi), 4, 0.70)
+
+
+def test_align_pairs_batched_vs_reference(engine, ref):
+    """fcx_align_pairs (graph_to_contig.get_aln_data: DWA.align(.., 1500, 1)) against the compiled reference."""
+    rng = np.random.default_rng(41)
+    seqs, want, q_ids, t_ids = [], [], [], []
+    for i in range(12):
+        g = synth.random_codes(int(rng.integers(800, 6000)), rng)
+        a = synth.codes_to_bytes(g)
+        b = synth.codes_to_bytes(synth.add_errors(g, rng, 0.02 * (i % 4), 0.02 * (i % 3), 0.01))
+        q_ids.append(len(seqs)); seqs.append(b)
+        t_ids.append(len(seqs)); seqs.append(a)
+        r = ref.align(b, a, 1500)
+        want.append((r["aln_str_size"], r["dist"], r["q_e"], r["t_e"]))
+    engine.upload_pool(seqs)
+    got = engine.align_pairs(q_ids, t_ids, None, 1500)
+    for i, w in enumerate(want):
+        assert tuple(int(x) for x in got[i]) == (w if w[0] else (0, 0, 0, 0)), i
+
+
+def test_capacity_retry_paths(oracle):
+    """Vote overflow arena and consensus record arena that start far too small: the wave is retried with
+    larger arenas instead of failing the call (the reference reallocs)."""
+    from falcon_b200.binding import Engine
+    e = Engine(0)
+    try:
+        e.set_option("debug_tiny_capacity", 1)
+        S = synth.make_set(40000, 3000, 30, seed=51, n_blocks=3)
+        e.upload_pool(S.pool)
+        got = e.consensus_blocks([b.tolist() for b in S.blocks], 4, 0.70)
+        for bi in range(len(S.blocks)):
+            assert got[bi] == oracle.generate_consensus(S.block_seqs(bi), 4, 0.70)
+    finally:
+        e.close()
+
+
+def test_many_full_size_blocks_vs_compiled_reference(engine, ref):
+    """64 full-size blocks (15 kb reads, 50x, BASELINE config 2 geometry) against oracle/_ref/falcon.so --
+    the unmodified reference C -- not the restatement."""
+    S = synth.make_set(4_600_000, 15000, 50, n_blocks=64, max_n_read=200, block_stride=239)
+    engine.upload_pool(S.pool)
+    got = engine.consensus_blocks([b.tolist() for b in S.blocks], 4, 0.70)
+    from concurrent.futures import ThreadPoolExecutor
+    import os as _os
+    # the reference is not re-entrant (static msa_array): fork workers, as falcon_kit does
+    import multiprocessing as mp
+    jobs = [(S.block_seqs(bi), 4, 0.70) for bi in range(len(S.blocks))]
+    with mp.get_context("fork").Pool(min(16, len(_os.sched_getaffinity(0)))) as pool:
+        want = pool.starmap(_ref_block, jobs)
+    for bi, w in enumerate(want):
+        assert got[bi] == w, "block %d" % bi
+
+
+def _ref_block(seqs, min_cov, min_idt):
+    from oracle.oracle import Ref
+    return Ref().generate_consensus(seqs, min_cov, min_idt)
+
+
+def test_rare_paths_also_covered_on_the_gpu(engine, oracle):
+    """The bodies of the emulator-only tests (wide DP bands, > 15 and > 32 links per position, deep
+    pile-up of > 256 pairs) run against the real device."""
+    import test_emu_parity as E
+    E.test_wide_bands_stay_exact(engine, oracle)
+    E.test_deep_coverage_overflows_the_position_slots(engine, oracle)
+    E.test_deep_noisy_pileup_takes_the_chunked_consensus_path(engine, oracle)
+
+
+def test_round1_dp_variants_still_agree(oracle):
+    """dp_variant 1 (k_dp) and 2 (k_dp with TMA-staged spans) + k_traceback_walk."""
+    from falcon_b200.binding import Engine
+    S = synth.make_set(40000, 4000, 20, seed=61, n_blocks=3)
+    for variant in (1, 2):
+        e = Engine(0)
+        try:
+            e.set_option("dp_variant", variant)
+            _check_set(e, oracle, S, min_cov=4)
+        finally:
+            e.close()
