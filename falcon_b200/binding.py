@@ -139,6 +139,20 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     lib.fcx_parser_take.argtypes = [C.c_void_p, C.c_uint32, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                     C.POINTER(C.c_uint32), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                     C.POINTER(C.c_uint32), C.POINTER(C.c_void_p)]
+    lib.fcx_dazz_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+    lib.fcx_dazz_close.argtypes = [C.c_void_p]
+    lib.fcx_dazz_last_error.argtypes = [C.c_void_p]
+    lib.fcx_dazz_last_error.restype = C.c_char_p
+    lib.fcx_dazz_nreads.argtypes = [C.c_void_p]
+    lib.fcx_dazz_nreads.restype = C.c_uint32
+    lib.fcx_dazz_read_length.argtypes = [C.c_void_p, C.c_uint32]
+    lib.fcx_dazz_read_length.restype = C.c_int32
+    lib.fcx_dazz_upload.argtypes = [C.c_void_p, C.c_void_p]
+    lib.fcx_las_open.argtypes = [C.c_void_p, C.c_char_p]
+    lib.fcx_las_take.argtypes = [C.c_void_p, C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_uint32, C.c_uint64,
+                                 C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_uint32), C.POINTER(C.c_void_p),
+                                 C.POINTER(C.c_int)]
+    lib.fcx_pool_upload_bps.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32]
     lib.fcx_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
     lib.fcx_timer_start.argtypes = [C.c_void_p]
     lib.fcx_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
@@ -230,7 +244,7 @@ class Engine:
         n = offsets.shape[0] - 1
         self._check(self._lib.fcx_pool_upload(self._h, bases_ptr, offsets.ctypes.data, n),
                     "fcx_pool_upload")
-        self.n_reads = n
+        self.n_reads = self._reserved = n
 
     def upload_pool(self, reads: Sequence[bytes]):
         offsets = np.zeros(len(reads) + 1, dtype=np.uint64)
@@ -385,7 +399,7 @@ class MultiEngine(Engine):
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         n = offsets.shape[0] - 1
         self._check(self._lib.fcx_multi_pool_upload(self._h, bases_ptr, offsets.ctypes.data, n), "fcx_multi_pool_upload")
-        self.n_reads = n
+        self.n_reads = self._reserved = n
 
     def peer_bytes(self) -> int:
         return int(self._lib.fcx_multi_peer_bytes(self._h))
@@ -466,3 +480,60 @@ class StreamParser:
             ids.append(sid.decode())
             addr += len(sid) + 1
         return b.value, offsets, block_off, read_ids, ids
+
+
+class DazzDB:
+    """A Dazzler read database + .las files read directly (fcx_dazz_*): replaces
+    `LA4Falcon -H$CUTOFF -fo db las | ...` (falcon_kit/mains/consensus_task.py:81-90)."""
+
+    def __init__(self, db_path: str, library: Optional[C.CDLL] = None):
+        self._lib = library or lib()
+        h = C.c_void_p()
+        if self._lib.fcx_dazz_open(os.fsencode(db_path), C.byref(h)) != 0:
+            raise EngineError("fcx_dazz_open: %s" % self._lib.fcx_dazz_last_error(None).decode())
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.fcx_dazz_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise EngineError("%s: %s" % (what, self._lib.fcx_dazz_last_error(self._h).decode()))
+
+    @property
+    def n_reads(self) -> int:
+        return int(self._lib.fcx_dazz_nreads(self._h))
+
+    def upload(self, engine: "Engine"):
+        """Every read of the DB into the engine's pool: id 2r forward, 2r + 1 reverse complement."""
+        self._check(self._lib.fcx_dazz_upload(self._h, engine._h), "fcx_dazz_upload")
+        engine.n_reads = engine._reserved = 2 * self.n_reads
+
+    def open_las(self, las_path: str):
+        self._check(self._lib.fcx_las_open(self._h, os.fsencode(las_path)), "fcx_las_open")
+
+    def take(self, seed_cutoff: int, min_n_read: int, min_len_aln: int, max_n_read: int, min_cov_aln: int,
+             max_cov_aln: int, max_blocks: int, max_pairs: int):
+        """-> (block_off, read_ids, seed_ids, done)"""
+        bo, ri, sid, nb, done = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_uint32(), C.c_int()
+        self._check(self._lib.fcx_las_take(self._h, seed_cutoff, min_n_read, min_len_aln, max_n_read, min_cov_aln,
+                                           max_cov_aln, max_blocks, max_pairs, C.byref(bo), C.byref(ri), C.byref(nb),
+                                           C.byref(sid), C.byref(done)), "fcx_las_take")
+        n = nb.value
+        block_off = np.ctypeslib.as_array((C.c_uint32 * (n + 1)).from_address(bo.value)).copy()
+        n_ids = int(block_off[-1])
+        read_ids = np.ctypeslib.as_array((C.c_uint32 * max(1, n_ids)).from_address(ri.value)).copy()[:n_ids]
+        ids, p = [], sid.value
+        for _ in range(n):
+            t = C.string_at(p)
+            ids.append(t.decode())
+            p += len(t) + 1
+        return block_off, read_ids, ids, bool(done.value)

@@ -93,6 +93,12 @@ def parse_args(argv):
     parser.add_argument("--stream", action="append", default=None, metavar="IN:OUT",
                         help="read LA4Falcon text from IN and write its FASTA to OUT instead of stdin/stdout; repeat the "
                              "option to serve several producers (files or named pipes) with this one GPU process")
+    parser.add_argument("--db", type=str, default=None,
+                        help="read a Dazzler DB directly (with --las) instead of LA4Falcon text on stdin: the whole read "
+                             "store is uploaded once, 2-bit packed, and the .las overlap records are turned into seed "
+                             "blocks with LA4Falcon's -f -o -H rules")
+    parser.add_argument("--las", action="append", default=None, metavar="FILE", help=".las file(s) for --db, processed in order")
+    parser.add_argument("-H", "--seed-cutoff", type=int, default=0, help="LA4Falcon's -H: only reads at least this long are seeds")
     parser.add_argument("--batch-blocks", type=int, default=1024, help="seed blocks per GPU batch")
     parser.add_argument("--batch-bases", type=int, default=1 << 30, help="read bases per GPU batch")
     return parser.parse_args(_normalise_flags(argv[1:]))
@@ -192,6 +198,39 @@ def run_native_parser(args, streams, engine):
             ps.close()
 
 
+def run_dazz(args, engine, out):
+    """--db / --las: Dazzler files in, FASTA out."""
+    from .binding import DazzDB
+    if not args.las:
+        raise SystemExit("--db needs at least one --las")
+    if not hasattr(engine, "trim_blocks_raw"):
+        raise SystemExit("--db runs on one device: use --device instead of --devices")
+    db = DazzDB(args.db, getattr(engine, "_lib", None))
+    try:
+        db.upload(engine)
+        n_store = engine.n_reads
+        for las in args.las:
+            db.open_las(las)
+            done = False
+            while not done:
+                block_off, read_ids, ids, done = db.take(args.seed_cutoff, args.min_n_read, args.min_len_aln, args.max_n_read,
+                                                         args.min_cov_aln, args.max_cov_aln, args.batch_blocks, 1 << 22)
+                if not ids:
+                    continue
+                if args.trim:
+                    block_off, read_ids = engine.trim_blocks_raw(block_off, read_ids, args.edge_tolerance, args.trim_size,
+                                                                 args.max_n_read, args.max_cov_aln)
+                data, off = engine.consensus_blocks_raw(block_off, read_ids, args.min_cov, args.min_idt, K)
+                if args.trim:
+                    engine.pool_truncate(n_store)
+                raw = data.tobytes()
+                for i, sid in enumerate(ids):
+                    emit(out, raw[int(off[i]):int(off[i + 1])].decode(), sid, args)
+    finally:
+        db.close()
+    out.flush()
+
+
 def run(args, stdin=None, stdout=None, engine=None):
     logging.basicConfig(level=int(round(10 * args.verbose_level)))
     stdin = stdin if stdin is not None else sys.stdin.buffer
@@ -208,6 +247,8 @@ def run(args, stdin=None, stdout=None, engine=None):
             engine = Engine(dev)
     if args.trim and not hasattr(engine, "trim_blocks_raw"):
         raise SystemExit("--trim runs on one device: use --device instead of --devices")
+    if getattr(args, "db", None):
+        return run_dazz(args, engine, stdout)
     streams, opened = [(stdin, stdout)], []
     if getattr(args, "stream", None):
         # several LA4Falcon producers feeding this one process (which owns the GPUs):

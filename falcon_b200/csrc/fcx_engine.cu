@@ -357,6 +357,74 @@ extern "C" int fcx_pool_upload(fcx_ctx* ctx, const char* bases, const uint64_t* 
     return 0;
 }
 
+// Pool from a Dazzler .bps image (fcx_dazz.cu): 2 entries per read, forward and reverse complement.
+extern "C" int fcx_pool_upload_bps(fcx_ctx* ctx, const uint8_t* bps, uint64_t n_bytes, const uint64_t* boff,
+                                   const int32_t* rlen, uint32_t n_reads) {
+    CK(cudaSetDevice(ctx->device));
+    if ((uint64_t)n_reads * 2 > 0xfffffff0ull) { ctx->err = "fcx_pool_upload_bps: too many reads"; return 1; }
+    const uint32_t ne = n_reads * 2;
+    std::vector<uint64_t> off((size_t)ne + 1, 0);
+    std::vector<int32_t> elen(ne);
+    for (uint32_t r = 0; r < n_reads; r++) {
+        if (rlen[r] < 0 || boff[r] + (uint64_t)(rlen[r] + 3) / 4 > n_bytes) { ctx->err = "fcx_pool_upload_bps: read outside the .bps image"; return 1; }
+        const int32_t l = rlen[r] > 100000 ? 99999 : rlen[r];               // consensus.py:178-179
+        elen[2 * r] = elen[2 * r + 1] = l;
+        off[2 * r + 1] = off[2 * r] + (uint64_t)l; off[2 * r + 2] = off[2 * r + 1] + (uint64_t)l;
+    }
+    uint64_t total_words = 0;
+    if (int rc = fcx_pool_reserve(ctx, off.data(), ne, &total_words)) return rc;
+    cudaStream_t st = ctx->stream;
+    DevBuf d_bps, d_boff, d_rlen, d_elen, d_woff;
+    auto fail = [&](const char* what, cudaError_t e) {
+        ctx->err = std::string(what) + ": " + cudaGetErrorString(e);
+        d_bps.release(); d_boff.release(); d_rlen.release(); d_elen.release(); d_woff.release();
+        return 1;
+    };
+    cudaError_t e;
+    if ((e = d_bps.reserve(n_bytes + 16)) != cudaSuccess) return fail("device memory for the .bps image", e);
+    if ((e = d_boff.reserve((size_t)n_reads * 8 + 8)) != cudaSuccess) return fail("cudaMalloc", e);
+    if ((e = d_rlen.reserve((size_t)n_reads * 4 + 4)) != cudaSuccess) return fail("cudaMalloc", e);
+    if ((e = d_elen.reserve((size_t)ne * 4 + 4)) != cudaSuccess) return fail("cudaMalloc", e);
+    if ((e = d_woff.reserve(((size_t)ne + 1) * 8)) != cudaSuccess) return fail("cudaMalloc", e);
+    // the image is usually an mmap of the .bps file: staged through pinned memory in 64 MB pieces
+    {
+        HostBuf stage[2];
+        const size_t piece = (size_t)64 << 20;
+        if ((e = stage[0].reserve(piece)) != cudaSuccess || (e = stage[1].reserve(piece)) != cudaSuccess) {
+            stage[0].release(); stage[1].release(); return fail("pinned staging memory", e);
+        }
+        cudaEvent_t ev[2]; cudaEventCreate(&ev[0]); cudaEventCreate(&ev[1]);
+        int k = 0;
+        for (uint64_t at = 0; at < n_bytes; at += piece, k ^= 1) {
+            const size_t n = (size_t)std::min<uint64_t>(piece, n_bytes - at);
+            cudaEventSynchronize(ev[k]);                               // the copy that last used this buffer
+            memcpy(stage[k].p, bps + at, n);
+            e = cudaMemcpyAsync((char*)d_bps.p + at, stage[k].p, n, cudaMemcpyHostToDevice, st);
+            cudaEventRecord(ev[k], st);
+            if (e != cudaSuccess) break;
+        }
+        cudaStreamSynchronize(st);
+        cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
+        stage[0].release(); stage[1].release();
+        if (e != cudaSuccess) return fail("upload of the .bps image", e);
+    }
+    if (n_reads) {
+        if ((e = cudaMemcpyAsync(d_boff.p, boff, (size_t)n_reads * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail("cudaMemcpyAsync", e);
+        if ((e = cudaMemcpyAsync(d_rlen.p, rlen, (size_t)n_reads * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail("cudaMemcpyAsync", e);
+        if ((e = cudaMemcpyAsync(d_elen.p, elen.data(), (size_t)ne * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail("cudaMemcpyAsync", e);
+        if ((e = cudaMemcpyAsync(d_woff.p, ctx->h_woff.data(), ((size_t)ne + 1) * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess) return fail("cudaMemcpyAsync", e);
+        if (total_words) {
+            FCX_LAUNCH(k_repack_bps, (unsigned)((total_words + 255) / 256), 256, 0, st, d_bps.as<uint8_t>(), d_boff.as<uint64_t>(),
+                       d_rlen.as<int32_t>(), d_elen.as<int32_t>(), d_woff.as<uint64_t>(), ne, total_words, ctx->d_pool.as<uint32_t>());
+            if ((e = cudaGetLastError()) != cudaSuccess) return fail("k_repack_bps", e);
+        }
+        if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return fail("k_repack_bps", e);
+    }
+    d_bps.release(); d_boff.release(); d_rlen.release(); d_elen.release(); d_woff.release();
+    ctx->n_reads = ne;
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------- waves
 namespace {
 
@@ -463,10 +531,16 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
         unsigned per_sm = (unsigned)std::max<size_t>(1, std::min<size_t>(2, (200 * 1024) / std::max<size_t>(rsmem, 1)));
         if (const char* e = getenv("FCX_RANGE_CTAS")) per_sm = (unsigned)std::max(1, atoi(e));
         const unsigned rgrid = std::min<unsigned>(nb, (unsigned)ctx->sm_count * per_sm);
-        CKR(L.d_rlist.reserve((size_t)rgrid * rwarps * RANGE_LIST_CAP * sizeof(uint32_t)));
+        // per-warp match list: expected hits = query k-mers x (seed positions per bucket + true hits);
+        // a list that still overflows (low-complexity sequence) takes the kernel's re-walking slow path
+        const double nq_max = max_rlen / 4.0 + 1;
+        int list_cap = (int)std::min<double>(1 << 20, std::max<double>(RANGE_LIST_CAP, 2.0 * nq_max * (max_slen / 65536.0 + 0.4)));
+        list_cap = (list_cap + 31) & ~31;
+        if (const char* e = getenv("FCX_RANGE_LIST_CAP")) list_cap = std::max(64, atoi(e) & ~31);
+        CKR(L.d_rlist.reserve((size_t)rgrid * rwarps * list_cap * sizeof(uint32_t)));
         FCX_LAUNCH(k_range, rgrid, rwarps * 32, rsmem, st,
             L.d_blocks.as<BlockDesc>(), nb, L.d_pairs.as<PairDesc>(), pool, L.d_ktab.as<uint32_t>(),
-            L.d_kpos.as<uint32_t>(), L.d_kbits.as<uint32_t>(), L.d_rlist.as<uint32_t>(), bins, L.d_ranges.as<PairRange>());
+            L.d_kpos.as<uint32_t>(), L.d_kbits.as<uint32_t>(), L.d_rlist.as<uint32_t>(), list_cap, bins, L.d_ranges.as<PairRange>());
         CKL(cudaGetLastError());
         L.counters[FCX_C_KERNEL_LAUNCHES] += 1;
         CKL(cudaMemcpyAsync(L.h_ranges.p, L.d_ranges.p, (size_t)np * sizeof(PairRange), cudaMemcpyDeviceToHost, st));

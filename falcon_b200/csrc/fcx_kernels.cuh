@@ -142,11 +142,44 @@ __global__ void k_pack(const uint8_t* __restrict__ ascii, const uint64_t* __rest
     if (bad) atomicOr(dirty, 1);
 }
 
+// ------------------------------------------------------------------------------ k_repack_bps
+// Dazzler .bps bytes (4 bases per byte, first base in the top two bits, a0 c1 g2 t3: DAZZ_DB
+// DB.c:Compress_Read) -> the engine's packed reads.  Pool entry e = 2r + c: read r forward (c = 0) or
+// reverse-complemented (c = 1), cut to `len` bases the way consensus.py:178-179 cuts the text
+// (the FIRST len characters of the oriented sequence).  One thread per output word.
+__global__ void k_repack_bps(const uint8_t* __restrict__ bps, const uint64_t* __restrict__ boff,
+                             const int32_t* __restrict__ rlen, const int32_t* __restrict__ elen,
+                             const uint64_t* __restrict__ woff, uint32_t n_entries, uint64_t total_words,
+                             uint32_t* __restrict__ packed) {
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= total_words) return;
+    uint32_t lo = 0, hi = n_entries;          // last e with woff[e] <= g
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (woff[mid] <= g) lo = mid; else hi = mid; }
+    const uint32_t e = lo, r = e >> 1;
+    const bool comp = (e & 1u) != 0;
+    const int full = rlen[r], len = elen[e];
+    const uint8_t* src = bps + boff[r];
+    const int64_t p0 = (int64_t)(g - woff[e]) * 16;
+    uint32_t word = 0;
+#pragma unroll
+    for (int b = 0; b < 16; b++) {
+        const int64_t p = p0 + b;
+        if (p < len) {
+            const int64_t sp = comp ? (int64_t)full - 1 - p : p;
+            uint32_t v = ((uint32_t)src[sp >> 2] >> (6 - 2 * (int)(sp & 3))) & 3u;
+            if (comp) v = 3u - v;
+            word |= v << (2 * b);
+        }
+    }
+    packed[g] = word;
+}
+
 // ------------------------------------------------------------------------------ k_index
 // One CTA per seed.  tab[] (65536 uint32, zeroed by the host) becomes, per bucket, the END offset
 // into kpos[]; bucket k spans [k ? tab[k-1] : 0, tab[k]), positions ascending -- the order the
 // reference's start/next chain yields (kmer_lookup.c:174-191, 257-282).  Positions 0..slen-9 are
 // indexed (loop bound `i < seq_len - K`).
+constexpr int INDEX_BIG_CAP = 3200;     // buckets of > 32 positions: at most 100000 / 33
 __global__ void __launch_bounds__(256) k_index(const BlockDesc* __restrict__ blocks,
                                                const uint32_t* __restrict__ pool,
                                                uint32_t* __restrict__ ktab,
@@ -180,21 +213,44 @@ __global__ void __launch_bounds__(256) k_index(const BlockDesc* __restrict__ blo
     uint32_t run = part[tid];
     for (int j = 0; j < 256; j++) { uint32_t v = mine[j]; mine[j] = run; run += v; }
     __syncthreads();
-    // stable fill by warp 0: tab[k] is the cursor of bucket k and ends as its END offset
-    if (tid < 32) {
-        volatile uint32_t* vtab = tab;
-        const unsigned lt = lanemask_lt();
+    // Fill.  tab[k] is the cursor of bucket k and ends as its END offset.  All threads scatter their
+    // positions with an atomic cursor (order inside a bucket arbitrary), then every bucket with two or
+    // more entries is put into ascending order -- the order the reference's start/next chain yields:
+    // small buckets (the rule: a 15 kb seed has < 1 position per bucket on average) by an insertion
+    // sort in the thread that owns the bucket, large ones (low-complexity seeds) by a warp that
+    // re-scans the seed and writes the positions of that k-mer in order.
+    for (int i = tid; i < n; i += 256) kpos[atomicAdd(&tab[fetch16(seed, i) & 0xffffu], 1u)] = (uint32_t)i;
+    __shared__ uint32_t s_big[INDEX_BIG_CAP];
+    __shared__ uint32_t s_nbig;
+    if (tid == 0) s_nbig = 0;
+    __syncthreads();
+    volatile uint32_t* vtab = tab;                 // (the cursors were advanced by atomics: read them past L1)
+    volatile uint32_t* vpos = kpos;
+    for (int k = tid; k < KTAB; k += 256) {
+        const uint32_t e = vtab[k], s0 = k ? vtab[k - 1] : 0u;
+        const uint32_t c = e - s0;
+        if (c < 2) continue;
+        if (c > 32) { const uint32_t at = atomicAdd(&s_nbig, 1u); if (at < INDEX_BIG_CAP) s_big[at] = (uint32_t)k; continue; }
+        for (uint32_t a = s0 + 1; a < e; a++) {
+            const uint32_t v = vpos[a];
+            uint32_t b = a;
+            while (b > s0 && vpos[b - 1] > v) { vpos[b] = vpos[b - 1]; b--; }
+            vpos[b] = v;
+        }
+    }
+    __syncthreads();
+    const uint32_t nbig = min(s_nbig, (uint32_t)INDEX_BIG_CAP);     // (more than INDEX_BIG_CAP buckets of > 32 positions
+    const int lane = tid & 31;                                      //  need a seed longer than 32 * INDEX_BIG_CAP)
+    const unsigned lt = lanemask_lt();
+    for (uint32_t j = tid >> 5; j < nbig; j += 8) {
+        const uint32_t k = s_big[j];
+        uint32_t w = k ? vtab[k - 1] : 0u;
         for (int b0 = 0; b0 < n; b0 += 32) {
-            int i = b0 + tid;
-            bool valid = i < n;
-            uint32_t kid = valid ? (fetch16(seed, i) & 0xffffu) : (0x10000u + tid);
-            unsigned peers = __match_any_sync(FULL, kid);
-            int rank = __popc(peers & lt);
-            uint32_t cur = valid ? vtab[kid] : 0;
-            if (valid) kpos[cur + rank] = (uint32_t)i;
-            __syncwarp();
-            if (valid && rank == 0) vtab[kid] = cur + __popc(peers);
-            __syncwarp();
+            const int i = b0 + lane;
+            const bool hit = i < n && (fetch16(seed, i) & 0xffffu) == k;
+            const unsigned hb = __ballot_sync(FULL, hit);
+            if (hit) kpos[w + __popc(hb & lt)] = (uint32_t)i;
+            w += __popc(hb);
         }
     }
 }
@@ -343,7 +399,7 @@ __device__ void range_pair_slow(const uint32_t* __restrict__ read, const uint32_
 // kmer_lookup.c:252-283) is materialised once into a per-warp global scratch, then the histogram,
 // arg-max and Kadane passes stream over it with coalesced loads.  Persistent warps: each warp owns
 // one scratch slot and loops over pairs.
-constexpr int RANGE_LIST_CAP = 16384;
+constexpr int RANGE_LIST_CAP = 16384;   // default capacity of the per-warp match list; the engine raises it for long reads
 
 // A match (query position i = 0, 4, 8, ... < 100000, seed position t < 100000) packed in 32 bits
 __device__ __forceinline__ uint32_t rm_pack(int i, int t) { return ((uint32_t)(i >> 2) << 17) | (uint32_t)t; }
@@ -358,14 +414,14 @@ __global__ void __launch_bounds__(RANGE_WARPS_MAX * 32)
 k_range(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, const PairDesc* __restrict__ pairs,
         const uint32_t* __restrict__ pool, const uint32_t* __restrict__ ktab,
         const uint32_t* __restrict__ kpos_arena, const uint32_t* __restrict__ kbits,
-        uint32_t* __restrict__ list_scratch, int bins, PairRange* __restrict__ out) {
+        uint32_t* __restrict__ list_scratch, int list_cap, int bins, PairRange* __restrict__ out) {
     FCX_DYN_SHARED(int, s_dyn_all);
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     uint32_t* sbits = reinterpret_cast<uint32_t*>(s_dyn_all);                 // KTAB / 32 words
     int* hist = s_dyn_all + KTAB / 32 + wib * bins;      // bins >= (max read len + max seed len) / 48 + 2 for this wave
     const int n_warps = (int)(blockDim.x >> 5);
     const uint32_t gw = blockIdx.x * n_warps + wib;
-    uint32_t* list = list_scratch + (size_t)gw * RANGE_LIST_CAP;
+    uint32_t* list = list_scratch + (size_t)gw * list_cap;
     const unsigned lt = lanemask_lt();
   for (uint32_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
     const BlockDesc bd = blocks[blk];
@@ -393,7 +449,7 @@ k_range(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, const PairDesc*
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += v; }
             const int total = __shfl_sync(FULL, incl, 31);
-            if (n + total > RANGE_LIST_CAP) { overflow = true; break; }
+            if (n + total > list_cap) { overflow = true; break; }
             int w = n + incl - c;
             for (uint32_t j = s; j < e; j++, w++) {
                 const int t = (int)__ldg(kpos + j);
@@ -444,7 +500,7 @@ k_range(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, const PairDesc*
             if (!kb) continue;
             const int excl = __popc(kb & lt), total = __popc(kb);
             if (!first_set) { const int fl = __ffs(kb) - 1; q0 = __shfl_sync(FULL, qi, fl); t0 = __shfl_sync(FULL, ti, fl); first_set = true; }
-            int sv = keep ? 32 * (idx_base + excl) - qi : INT_MAX;      // fits: idx < 16384, q < 100000
+            int sv = keep ? 32 * (idx_base + excl) - qi : INT_MAX;      // fits: idx < RANGE_LIST_CAP_MAX (2^20), q < 100000
             int src = lane;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {

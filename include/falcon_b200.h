@@ -198,6 +198,34 @@ int fcx_parser_take(fcx_parser *, uint32_t max_blocks, uint64_t max_bases, const
                     const uint64_t **offsets, uint32_t *n_reads, const uint32_t **block_off,
                     const uint32_t **read_ids, uint32_t *n_blocks, const char **seed_ids);
 
+/* ---------------------------------------------------------------- Dazzler DB + .las input
+ * Reads a Dazzler read database (<root>.db stub + hidden .<root>.idx / .<root>.bps) and a local
+ * alignment file (.las) directly, replacing the text hop `LA4Falcon -H$CUTOFF -fo db las | consensus`
+ * (falcon_kit/mains/consensus_task.py:81-90, falcon_kit/bash.py:349-358):
+ *   fcx_dazz_upload  puts every (trimmed) read of the DB into the engine's pool, 2-bit packed, in both
+ *                    orientations: pool id 2r = read r, 2r + 1 = its reverse complement;
+ *   fcx_las_take     walks the overlap records with LA4Falcon's -f -o -H<seed_cutoff> rules and the
+ *                    consensus parser's rules (falcon_kit/mains/consensus.py:161-209, :26-45) and
+ *                    returns seed blocks as lists of pool ids (seed ids formatted %08d as LA4Falcon
+ *                    prints them, NUL-separated), ready for fcx_consensus_blocks.
+ * File layouts restate DAZZ_DB's DB.h and DALIGNER's align.h; see fcx_dazz.cu for provenance. */
+typedef struct fcx_dazz fcx_dazz;
+int fcx_dazz_open(const char *db_path, fcx_dazz **out);
+void fcx_dazz_close(fcx_dazz *);
+const char *fcx_dazz_last_error(const fcx_dazz *);
+uint32_t fcx_dazz_nreads(const fcx_dazz *);
+int32_t fcx_dazz_read_length(const fcx_dazz *, uint32_t read);
+int fcx_dazz_upload(fcx_dazz *, fcx_ctx *);
+int fcx_las_open(fcx_dazz *, const char *las_path);
+int fcx_las_take(fcx_dazz *, int seed_cutoff, unsigned min_n_read, unsigned min_len_aln, unsigned max_n_read,
+                 unsigned min_cov_aln, unsigned max_cov_aln, uint32_t max_blocks, uint64_t max_pairs,
+                 const uint32_t **block_off, const uint32_t **read_ids, uint32_t *n_blocks,
+                 const char **seed_ids, int *done);
+/* Pool from a .bps image: n_reads reads of rlen[r] bases whose compressed bases start at byte boff[r];
+ * 2 * n_reads pool entries (forward, reverse complement), each cut like consensus.py:178-179. */
+int fcx_pool_upload_bps(fcx_ctx *, const uint8_t *bps, uint64_t n_bytes, const uint64_t *boff,
+                        const int32_t *rlen, uint32_t n_reads);
+
 /* Engine options: "pair_info" (0/1, keep per-pair diagnostics; default 1), "arena_gb" (device
  * memory budget for wave buffers), "max_wave_blocks", "min_wave_blocks", "lanes" (waves in flight,
  * 1..FCX_LANES; with 1 the per-kernel timings of fcx_last_stats are not inflated by overlap),

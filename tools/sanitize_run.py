@@ -33,8 +33,19 @@ for r in range(8):
     reads.append(synth.codes_to_bytes(np.concatenate([x[:1500], synth.random_codes(12, rng), x[1500:]])))
 seqs = [seed, seed] + reads
 ok &= eng.generate_consensus(seqs, 2, 0.70) == orc.generate_consensus(seqs, 2, 0.70)
-eng.set_option("dp_staged", 1)
-ok &= eng.generate_consensus(seqs, 2, 0.70) == orc.generate_consensus(seqs, 2, 0.70)
+for variant in (2, 1, 3):                       # TMA-staged k_dp, plain k_dp (+ k_traceback_walk), back to k_dp3
+    eng.set_option("dp_variant", variant)
+    ok &= eng.generate_consensus(seqs, 2, 0.70) == orc.generate_consensus(seqs, 2, 0.70)
+# device-side --trim (k_trim_range, k_subreads) and the batched distance-only align
+S = synth.make_set(30000, 3000, 14, seed=21, n_blocks=2)
+eng.upload_pool(S.pool)
+boff = np.zeros(len(S.blocks) + 1, dtype=np.uint32)
+np.cumsum([len(b) for b in S.blocks], out=boff[1:])
+noff, nids = eng.trim_blocks_raw(boff, np.concatenate(S.blocks).astype(np.uint32))
+eng.consensus_blocks([nids[int(noff[b]):int(noff[b + 1])].tolist() for b in range(len(S.blocks))], 4, 0.70)
+eng.pool_truncate(len(S.pool))
+res = eng.align_pairs([2, 3], [0, 0], None, 1500)
+ok &= int(res[0][0]) == orc.align(S.pool[2], S.pool[0], 1500)["aln_str_size"]
 L = lib()
 p = L.align(reads[0], len(reads[0]), seed, len(seed), 150, 1)
 ok &= p[0].aln_str_size == orc.align(reads[0], seed)["aln_str_size"]
