@@ -530,7 +530,8 @@ class DazzDB:
         n = nb.value
         block_off = np.ctypeslib.as_array((C.c_uint32 * (n + 1)).from_address(bo.value)).copy()
         n_ids = int(block_off[-1])
-        read_ids = np.ctypeslib.as_array((C.c_uint32 * max(1, n_ids)).from_address(ri.value)).copy()[:n_ids]
+        read_ids = (np.ctypeslib.as_array((C.c_uint32 * n_ids).from_address(ri.value)).copy() if n_ids
+                    else np.zeros(0, dtype=np.uint32))
         ids, p = [], sid.value
         for _ in range(n):
             t = C.string_at(p)

@@ -103,7 +103,8 @@ def test_bad_files_are_reported(tmp_path):
     e = emu_engine()
     with pytest.raises(EngineError):
         DazzDB(str(tmp_path / "missing.db"), e._lib)
-    reads, overlaps, db, las = make_case(tmp_path, n_reads=5, read_len=600)
+    reads, overlaps, db, las = make_case(tmp_path, n_reads=12, read_len=2000)
+    assert len(overlaps) > 2
     idx = os.path.join(str(tmp_path), ".reads.idx")
     blob = open(idx, "rb").read()
     open(idx, "wb").write(blob[:-8])
