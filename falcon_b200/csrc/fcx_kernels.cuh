@@ -180,6 +180,7 @@ __global__ void k_repack_bps(const uint8_t* __restrict__ bps, const uint64_t* __
 // reference's start/next chain yields (kmer_lookup.c:174-191, 257-282).  Positions 0..slen-9 are
 // indexed (loop bound `i < seq_len - K`).
 constexpr int INDEX_BIG_CAP = 3200;     // buckets of > 32 positions: at most 100000 / 33
+constexpr int INDEX_MULTI_CAP = 8192;   // buckets with >= 2 positions listed in shared memory (16 KB)
 __global__ void __launch_bounds__(256) k_index(const BlockDesc* __restrict__ blocks,
                                                const uint32_t* __restrict__ pool,
                                                uint32_t* __restrict__ ktab,
@@ -195,6 +196,11 @@ __global__ void __launch_bounds__(256) k_index(const BlockDesc* __restrict__ blo
     // goes to the 256 KB table for the ~1 in 4 query k-mers that can have a hit
     uint32_t* bits = kbits + (size_t)blockIdx.x * (KTAB / 32);
     if (n <= 0) { for (int j = tid; j < KTAB / 32; j += 256) bits[j] = 0u; return; }
+    // buckets with two or more positions are listed (by the scan below): only they need ordering later
+    __shared__ uint16_t s_multi[INDEX_MULTI_CAP];
+    __shared__ uint32_t s_nmulti, s_nbig;
+    if (tid == 0) { s_nmulti = 0; s_nbig = 0; }
+    __syncthreads();
     for (int i = tid; i < n; i += 256) atomicAdd(&tab[fetch16(seed, i) & 0xffffu], 1u);
     __syncthreads();
     // exclusive scan, 256 entries per thread
@@ -211,7 +217,10 @@ __global__ void __launch_bounds__(256) k_index(const BlockDesc* __restrict__ blo
     if (tid == 0) { uint32_t run = 0; for (int j = 0; j < 256; j++) { uint32_t v = part[j]; part[j] = run; run += v; } }
     __syncthreads();
     uint32_t run = part[tid];
-    for (int j = 0; j < 256; j++) { uint32_t v = mine[j]; mine[j] = run; run += v; }
+    for (int j = 0; j < 256; j++) {
+        const uint32_t v = mine[j]; mine[j] = run; run += v;
+        if (v >= 2u) { const uint32_t at = atomicAdd(&s_nmulti, 1u); if (at < INDEX_MULTI_CAP) s_multi[at] = (uint16_t)(tid * 256 + j); }
+    }
     __syncthreads();
     // Fill.  tab[k] is the cursor of bucket k and ends as its END offset.  All threads scatter their
     // positions with an atomic cursor (order inside a bucket arbitrary), then every bucket with two or
@@ -220,17 +229,19 @@ __global__ void __launch_bounds__(256) k_index(const BlockDesc* __restrict__ blo
     // sort in the thread that owns the bucket, large ones (low-complexity seeds) by a warp that
     // re-scans the seed and writes the positions of that k-mer in order.
     for (int i = tid; i < n; i += 256) kpos[atomicAdd(&tab[fetch16(seed, i) & 0xffffu], 1u)] = (uint32_t)i;
-    __shared__ uint32_t s_big[INDEX_BIG_CAP];
-    __shared__ uint32_t s_nbig;
-    if (tid == 0) s_nbig = 0;
+    __shared__ uint16_t s_big[INDEX_BIG_CAP];
     __syncthreads();
     volatile uint32_t* vtab = tab;                 // (the cursors were advanced by atomics: read them past L1)
     volatile uint32_t* vpos = kpos;
-    for (int k = tid; k < KTAB; k += 256) {
+    const uint32_t nmulti = s_nmulti;
+    const bool listed = nmulti <= INDEX_MULTI_CAP;  // otherwise (long, repetitive seeds) every bucket is looked at
+    const int n_todo = listed ? (int)nmulti : KTAB;
+    for (int t = tid; t < n_todo; t += 256) {
+        const int k = listed ? (int)s_multi[t] : t;
         const uint32_t e = vtab[k], s0 = k ? vtab[k - 1] : 0u;
         const uint32_t c = e - s0;
         if (c < 2) continue;
-        if (c > 32) { const uint32_t at = atomicAdd(&s_nbig, 1u); if (at < INDEX_BIG_CAP) s_big[at] = (uint32_t)k; continue; }
+        if (c > 32) { const uint32_t at = atomicAdd(&s_nbig, 1u); if (at < INDEX_BIG_CAP) s_big[at] = (uint16_t)k; continue; }
         for (uint32_t a = s0 + 1; a < e; a++) {
             const uint32_t v = vpos[a];
             uint32_t b = a;

@@ -43,55 +43,58 @@ __device__ __forceinline__ uint32_t lk_key(int delta, int base, uint32_t pred) {
 
 // Slot layout (uint2 units): slot[0] = {n_links << 16 | coverage (<= 65535), overflow offset};
 // slot[1..15] = links {key, count}; links 15.. live in the overflow arena at `overflow offset`.
-// Writes position i's links, stably sorted by delta (the DP needs a level complete before the next).
-__device__ __forceinline__ void vote_write_slot(const uint32_t* key, const uint32_t* cnt, int n, int coverage, const int maxd,
-                                                uint2* __restrict__ slot, uint2* __restrict__ ovf_arena, uint32_t ovf_cap,
-                                                uint32_t* __restrict__ ovf_next, int* __restrict__ err_flag) {
-    uint2* ovf = nullptr; uint32_t ovf_off = 0;
-    if (n > VSLOT - 1) {
-        ovf_off = atomicAdd(ovf_next, (uint32_t)(n - (VSLOT - 1)));
-        if (ovf_off + (uint32_t)(n - (VSLOT - 1)) > ovf_cap) { atomicMax(err_flag, 2); n = 0; coverage = 0; }
-        else ovf = ovf_arena + ovf_off;
-    }
-    slot[0] = make_uint2(((uint32_t)n << 16) | (uint32_t)coverage, ovf_off);
-    int w = 0;
-    for (int lev = 0; lev <= maxd && w < n; lev++)
-        for (int e = 0; e < n; e++)
-            if ((int)(key[e] >> 16) == lev) {
-                const uint2 v = make_uint2(key[e], cnt[e]);
-                if (w < VSLOT - 1) slot[1 + w] = v; else ovf[w - (VSLOT - 1)] = v;
-                w++;
-            }
-}
-
-// One position voted by ONE THREAD over all reads of the block (private link table in local memory,
-// linear search): the fallback for positions with more than VT_CAP distinct links.
-__device__ FCX_NOINLINE void vote_position_slow(const BlockDesc& bd, const int i, const VoteMeta* __restrict__ vmeta,
-                                                const uint32_t* __restrict__ pool, const uint32_t* __restrict__ xck_arena,
-                                                const uint32_t* __restrict__ ent_arena, uint2* __restrict__ slot_arena,
-                                                uint2* __restrict__ ovf_arena, uint32_t ovf_cap, uint32_t* __restrict__ ovf_next,
-                                                int* __restrict__ err_flag) {
+__global__ void __launch_bounds__(VOTE_TP)
+k_vote(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, uint32_t n_tiles,
+       const VoteMeta* __restrict__ vmeta, const uint32_t* __restrict__ pool,
+       const uint32_t* __restrict__ xck_arena, const uint32_t* __restrict__ ent_arena,
+       uint2* __restrict__ slot_arena, uint2* __restrict__ ovf_arena, uint32_t ovf_cap,
+       uint32_t* __restrict__ ovf_next, int* __restrict__ err_flag) {
+    const uint32_t T = blockIdx.x;
+    if (T >= n_tiles) return;
+    uint32_t lo = 0, hi = n_blocks;                 // last block with tile_begin <= T
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (blocks[mid].tile_begin <= T) lo = mid; else hi = mid; }
+    const BlockDesc bd = blocks[lo];
+    const int i0 = (int)(T - bd.tile_begin) * VOTE_TP;
+    const int i = i0 + (int)threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool in_seed = i < bd.slen;
     const uint32_t* seed = pool + bd.seed_woff;
-    const int Si = base_at(seed, i);
-    const int Sp = i > 0 ? base_at(seed, i - 1) : 0;
+    const int Si = in_seed ? base_at(seed, i) : 0;
+    const int Sp = (in_seed && i > 0) ? base_at(seed, i - 1) : 0;
+
     uint32_t key[VCAP]; uint32_t cnt[VCAP];         // private link table, first-appearance order
     int n = 0, coverage = 0, maxd = 0; bool overflow = false;
+    // the dominant link "match after a plain match" is counted in a register; its table slot is
+    // reserved when it first appears so that the order stays the reference's
+    const uint32_t k_dom = lk_key(0, Si, (uint32_t)Sp);
+    int idx_dom = -1; uint32_t c_dom = 0;
     auto vote = [&](const uint32_t k) {
+        if (k == k_dom) {
+            if (idx_dom < 0) { if (n < VCAP) { idx_dom = n; key[n] = k; cnt[n] = 0; n++; } else overflow = true; }
+            c_dom++;
+            return;
+        }
         for (int e = 0; e < n; e++) if (key[e] == k) { cnt[e]++; return; }
         if (n < VCAP) { key[n] = k; cnt[n] = 1; n++; } else overflow = true;
     };
+
     for (uint32_t j = 0; j < bd.n_pairs; j++) {
-        const VoteMeta vm = vmeta[bd.pair_begin + j];
+        const VoteMeta vm = vmeta[bd.pair_begin + j];                    // same for the whole CTA
         if (vm.t_cnt == 0) continue;                                     // pair not accepted
+        if (vm.t_start >= i0 + VOTE_TP || vm.t_start + vm.t_cnt <= i0) continue;   // does not touch this tile
         const int y = i - vm.t_start;
-        if (y < 0 || y >= vm.t_cnt) continue;
+        const bool act = in_seed && y >= 0 && y < vm.t_cnt;
         const uint32_t* ent = ent_arena + vm.ent_off;
-        const uint32_t ec = __ldg(ent + y);
-        const uint32_t ep = y > 0 ? __ldg(ent + y - 1) : 0u;
+        const uint32_t ec = act ? __ldg(ent + y) : 0u;
+        // the read's entry at position i - 1: the left neighbour thread holds it
+        uint32_t ep = __shfl_up_sync(FULL, ec, 1);
+        if (lane == 0) ep = (act && y > 0) ? __ldg(ent + y - 1) : 0u;
+        if (!act) continue;
         coverage++;
         const int m = (ec & ENT_MATCH) ? 1 : 0, nins = ent_nins(ec);
         const int b0 = m ? Si : 4;
-        int x = -1;                          // query index at this column: only needed beyond the 11 inline inserted bases
+        // query index at this column: only needed to fetch inserted bases beyond the 11 inline ones
+        int x = -1;
         const uint32_t* qr = pool + vm.q_woff;
         uint32_t pred = LK_START;
         if (y > 0) {
@@ -114,159 +117,26 @@ __device__ FCX_NOINLINE void vote_position_slow(const BlockDesc& bd, const int i
             }
         }
     }
+    if (!in_seed) return;
+    if (idx_dom >= 0) cnt[idx_dom] = c_dom;
     if (overflow) { atomicMax(err_flag, 1); n = 0; coverage = 0; }
-    vote_write_slot(key, cnt, n, coverage, maxd, slot_arena + (bd.slot_off + (uint64_t)i) * VSLOT, ovf_arena, ovf_cap, ovf_next, err_flag);
-}
-
-// ------------------------------------------------------------------------------ k_vote
-// One WARP per tile of 32 seed positions.  The accepted reads of the block that touch the tile are
-// taken 32 at a time (in read order): lane r stages its read's 33 entries ent[y0-1 .. y0+31] in
-// shared memory, then the warp walks the 32 positions with lane = READ: every lane forms the link
-// key its read casts at the position, ONE __match_any_sync groups equal keys (count = popcount,
-// first appearance = lowest lane = first read), and the group leaders merge (key, count) into the
-// position's table in shared memory (lanes compare table entries in parallel).  Insertion levels are
-// further rounds of the same.  At the end lane p writes position p's slot.  A position that needs
-// more than VT_CAP table entries is redone by vote_position_slow.
-constexpr int VT_CAP = 32;           // table entries per position in shared memory (searched one per lane)
-constexpr int VT_STRIDE = 33;        // padded row length: conflict-free for lane = position and lane = entry
-
-__global__ void __launch_bounds__(VOTE_TP)
-k_vote(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, uint32_t n_tiles,
-       const VoteMeta* __restrict__ vmeta, const uint32_t* __restrict__ pool,
-       const uint32_t* __restrict__ xck_arena, const uint32_t* __restrict__ ent_arena,
-       uint2* __restrict__ slot_arena, uint2* __restrict__ ovf_arena, uint32_t ovf_cap,
-       uint32_t* __restrict__ ovf_next, int* __restrict__ err_flag) {
-    constexpr int NW = VOTE_TP / 32;
-    __shared__ uint32_t s_ent[NW][32 * 33];            // [read][0] = entry left of the tile, [read][1 + p]
-    __shared__ uint32_t s_key[NW][32 * VT_STRIDE];     // [position][entry]
-    __shared__ uint16_t s_cnt[NW][32 * VT_STRIDE];     // (a block has at most 65000 reads)
-    __shared__ uint32_t s_grp[NW][64];                 // pair indices of the group being filled (+ spill-over)
-    const uint32_t T = blockIdx.x;
-    if (T >= n_tiles) return;
-    uint32_t lo = 0, hi = n_blocks;                 // last block with tile_begin <= T
-    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (blocks[mid].tile_begin <= T) lo = mid; else hi = mid; }
-    const BlockDesc bd = blocks[lo];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int pos0 = (int)(T - bd.tile_begin) * VOTE_TP + 32 * wib;        // first position of this warp's tile
-    if (pos0 >= bd.slen) return;                                           // (no CTA-wide barrier below)
-    const uint32_t* seed = pool + bd.seed_woff;
-    const unsigned lt = lanemask_lt();
-    uint32_t* ent_t = s_ent[wib]; uint32_t* tkey = s_key[wib]; uint16_t* tcnt = s_cnt[wib]; uint32_t* grp = s_grp[wib];
-    // lane p owns position pos0 + p when it comes to the seed bases, the counters and the output
-    const int my_i = pos0 + lane;
-    const bool in_seed = my_i < bd.slen;
-    const int my_S = in_seed ? base_at(seed, my_i) : 0;
-    const int my_Sp = (in_seed && my_i > 0) ? base_at(seed, my_i - 1) : 0;
-    int my_n = 0, my_cov = 0, my_maxd = 0;         // table size, coverage, deepest level of MY position
-    bool too_many = false;
-
-    auto process_group = [&](const int count) {
-        // ---- stage: lane r = read grp[r]
-        VoteMeta vm; vm.ent_off = 0; vm.q_woff = 0; vm.t_start = 0; vm.t_cnt = 0; vm.q_s = 0; vm.xck_off = 0;
-        if (lane < count) vm = vmeta[bd.pair_begin + grp[lane]];
-        const int y0 = pos0 - vm.t_start;                                  // the read's column at the tile's first position
-        const uint32_t* ent = ent_arena + vm.ent_off;
-        for (int c = 0; c < 33; c++) {
-            const int y = y0 - 1 + c;
-            ent_t[lane * 33 + c] = (y >= 0 && y < vm.t_cnt) ? __ldg(ent + y) : 0u;
-        }
-        __syncwarp();
-        // ---- vote: positions in turn, lane = read
-        for (int p = 0; p < 32; p++) {
-            const uint32_t ec = ent_t[lane * 33 + p + 1];
-            const bool act = (ec & ENT_VALID) != 0;
-            const unsigned actm = __ballot_sync(FULL, act);
-            if (actm == 0u) continue;
-            const int Si = __shfl_sync(FULL, my_S, p), Sp = __shfl_sync(FULL, my_Sp, p);
-            int np = __shfl_sync(FULL, my_n, p);                            // table size of this position (uniform)
-            const int y = y0 + p;
-            const uint32_t ep = ent_t[lane * 33 + p];
-            const int m = (ec & ENT_MATCH) ? 1 : 0, nins = act ? ent_nins(ec) : 0;
-            const int b0 = m ? Si : 4;
-            int x = -1;
-            uint32_t pred = LK_START;
-            if (act && y > 0) {
-                const int pn = ent_nins(ep);
-                int pb;
-                if (pn == 0) pb = (ep & ENT_MATCH) ? Sp : 4;
-                else if (pn <= ENT_INS_INLINE) pb = ent_ins(ep, pn - 1);
-                else { x = xck_lookup(xck_arena + vm.xck_off, ent, y); pb = base_at(pool + vm.q_woff, vm.q_s + x - 1); }
-                pred = ((uint32_t)pn << 3) | (uint32_t)pb;
-            }
-            const int maxn = __reduce_max_sync(FULL, nins);
-            uint32_t key = lk_key(0, b0, pred);
-            int pb = b0;
-            bool on = act;
-            for (int lev = 0;; ) {
-                // one round: equal keys grouped, leaders merged into the table of position p
-                const unsigned peers = __match_any_sync(FULL, on ? key : (0xffff0000u | (uint32_t)lane));
-                unsigned leaders = __ballot_sync(FULL, on && (peers & lt) == 0u);      // first read casting each key, in read order
-                while (leaders) {
-                    const int ll = __ffs(leaders) - 1;
-                    leaders &= leaders - 1u;
-                    const uint32_t k = __shfl_sync(FULL, key, ll);
-                    const int c = __popc(__shfl_sync(FULL, peers, ll));
-                    const unsigned hit = __ballot_sync(FULL, lane < np && tkey[p * VT_STRIDE + lane] == k);
-                    if (hit) { if (lane == 0) tcnt[p * VT_STRIDE + __ffs(hit) - 1] += (uint16_t)c; }
-                    else {
-                        if (np < VT_CAP) { if (lane == 0) { tkey[p * VT_STRIDE + np] = k; tcnt[p * VT_STRIDE + np] = (uint16_t)c; } }
-                        np++;                                                      // (counts past VT_CAP only flag the overflow)
-                    }
-                    __syncwarp();
-                }
-                lev++;
-                if (lev > maxn) break;
-                on = act && nins >= lev;
-                if (on) {
-                    int bb;
-                    if (lev <= ENT_INS_INLINE) bb = ent_ins(ec, lev - 1);
-                    else {
-                        if (x < 0) x = xck_lookup(xck_arena + vm.xck_off, ent, y);
-                        bb = base_at(pool + vm.q_woff, vm.q_s + x + m + lev - 1);
-                    }
-                    key = lk_key(lev, bb, ((uint32_t)(lev - 1) << 3) | (uint32_t)pb);
-                    pb = bb;
-                }
-            }
-            if (lane == p) { my_n = np; my_cov += __popc(actm); my_maxd = max(my_maxd, maxn); }
-        }
-        __syncwarp();
-    };
-
-    // ---- the block's accepted reads that touch this tile, in read order, 32 at a time
-    int gn = 0;
-    for (uint32_t j0 = 0; j0 < bd.n_pairs; j0 += 32) {
-        const uint32_t j = j0 + lane;
-        bool touch = false;
-        if (j < bd.n_pairs) {
-            const VoteMeta vm = vmeta[bd.pair_begin + j];
-            touch = vm.t_cnt != 0 && vm.t_start < pos0 + 32 && vm.t_start + vm.t_cnt > pos0;
-        }
-        const unsigned tm = __ballot_sync(FULL, touch);
-        if (tm == 0u) continue;
-        if (touch) grp[gn + __popc(tm & lt)] = j;
-        gn += __popc(tm);
-        __syncwarp();
-        if (gn >= 32) {
-            process_group(32);
-            if (lane < gn - 32) grp[lane] = grp[32 + lane];
-            gn -= 32;
-            __syncwarp();
-        }
+    // ---- write the slot: links stably sorted by delta (the DP needs a level complete before the next)
+    uint2* slot = slot_arena + (bd.slot_off + (uint64_t)i) * VSLOT;
+    uint2* ovf = nullptr; uint32_t ovf_off = 0;
+    if (n > VSLOT - 1) {
+        ovf_off = atomicAdd(ovf_next, (uint32_t)(n - (VSLOT - 1)));
+        if (ovf_off + (uint32_t)(n - (VSLOT - 1)) > ovf_cap) { atomicMax(err_flag, 2); n = 0; coverage = 0; }
+        else ovf = ovf_arena + ovf_off;
     }
-    if (gn > 0) process_group(gn);
-
-    // ---- output: lane p writes position pos0 + p
-    too_many = my_n > VT_CAP;
-    if (__any_sync(FULL, too_many)) {                 // rare: deep, noisy pile-ups
-        if (in_seed && too_many)
-            vote_position_slow(bd, my_i, vmeta, pool, xck_arena, ent_arena, slot_arena, ovf_arena, ovf_cap, ovf_next, err_flag);
-    }
-    if (!in_seed || too_many) return;
-    uint32_t key[VT_CAP], cnt[VT_CAP];
-    for (int e = 0; e < my_n; e++) { key[e] = tkey[lane * VT_STRIDE + e]; cnt[e] = tcnt[lane * VT_STRIDE + e]; }
-    vote_write_slot(key, cnt, my_n, my_cov, my_maxd, slot_arena + (bd.slot_off + (uint64_t)my_i) * VSLOT, ovf_arena, ovf_cap,
-                    ovf_next, err_flag);
+    slot[0] = make_uint2(((uint32_t)n << 16) | (uint32_t)coverage, ovf_off);
+    int w = 0;
+    for (int lev = 0; lev <= maxd && w < n; lev++)
+        for (int e = 0; e < n; e++)
+            if ((int)(key[e] >> 16) == lev) {
+                const uint2 v = make_uint2(key[e], cnt[e]);
+                if (w < VSLOT - 1) slot[1 + w] = v; else ovf[w - (VSLOT - 1)] = v;
+                w++;
+            }
 }
 
 // ------------------------------------------------------------------------------ k_cns_dp
