@@ -987,22 +987,41 @@ k_traceback(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ p
         if (wi != wt_i) { wt_i = wi; wt_lo = __ldg(t + wi); wt_hi = __ldg(t + wi + 1); }
         return __funnelshift_r(wt_lo, wt_hi, (pos & 15) << 1);
     };
-    // output cursor: yo = number of entries emitted so far (entry yo goes to ent[yo])
+    // output cursor: yo = number of entries emitted so far (entry yo goes to ent[yo]).  Everything below
+    // is straight-line, predicated code: the 32 pairs of a warp take different turns at every step
+    // (deletion / insertion, snake lengths), so loops and branches here would serialise the lanes.
     int yo = 0; uint32_t b0 = 0, b1 = 0, b2 = 0;
-    auto emit = [&](const uint32_t e, const int xcol) {
-        if ((yo & 31) == 0) xck[yo >> 5] = (uint32_t)xcol;
+    auto emit1 = [&](const bool on, const uint32_t e, const int xcol) {      // one entry, if `on`
         const int r = yo & 3;
-        if (r == 3) *reinterpret_cast<uint4*>(ent + (yo - 3)) = make_uint4(b0, b1, b2, e);
-        b0 = r == 0 ? e : b0; b1 = r == 1 ? e : b1; b2 = r == 2 ? e : b2;
-        yo++;
+        if (on && (yo & 31) == 0) xck[yo >> 5] = (uint32_t)xcol;
+        if (on && r == 3) *reinterpret_cast<uint4*>(ent + (yo - 3)) = make_uint4(b0, b1, b2, e);
+        b0 = (on && r == 0) ? e : b0; b1 = (on && r == 1) ? e : b1; b2 = (on && r == 2) ? e : b2;
+        yo += on ? 1 : 0;
     };
-    auto close_pending = [&]() { if (open) emit(pend | ((uint32_t)run << 22), pend_x); };
+    auto plain_run = [&](const int L, const int xc) {                           // 0 <= L <= 16 plain match columns
+        const int r = yo & 3, total = r + L;
+        const int nx = (yo + 31) & ~31;                                         // a checkpoint column inside the run?
+        if (nx < yo + L) xck[nx >> 5] = (uint32_t)(xc + (nx - yo));
+        uint32_t* v = ent + (yo - r);
+        const bool spill = total >= 4;
+        if (spill) *reinterpret_cast<uint4*>(v) = make_uint4(r > 0 ? b0 : ENT_PLAIN, r > 1 ? b1 : ENT_PLAIN, r > 2 ? b2 : ENT_PLAIN, ENT_PLAIN);
+        const uint4 pl4 = make_uint4(ENT_PLAIN, ENT_PLAIN, ENT_PLAIN, ENT_PLAIN);
+        if (total >= 8) *reinterpret_cast<uint4*>(v + 4) = pl4;
+        if (total >= 12) *reinterpret_cast<uint4*>(v + 8) = pl4;
+        if (total >= 16) *reinterpret_cast<uint4*>(v + 12) = pl4;
+        // what remains open in the register buffer: entries (total & 3) of the last group
+        b0 = (spill || (r == 0 && total > 0)) ? ENT_PLAIN : b0;
+        b1 = (spill || (r <= 1 && total > 1)) ? ENT_PLAIN : b1;
+        b2 = (spill || (r <= 2 && total > 2)) ? ENT_PLAIN : b2;
+        yo += L;
+    };
     for (int d = 0; d <= D; d++) {
+        bool del = false;
         if (d > 0) {
             if ((d & 31) == 0 || d == 1) pw = path[d >> 5];
-            const bool del = ((pw >> (d & 31)) & 1u) != 0;          // target-only column
-            const uint32_t qb = win_q(qs + x) & 3u;                  // the query base of a query-only column
-            if (del) close_pending();
+            del = ((pw >> (d & 31)) & 1u) != 0;                          // target-only column
+            const uint32_t qb = win_q(qs + x) & 3u;                      // the query base of a query-only column
+            emit1(del && open, pend | ((uint32_t)run << 22), pend_x);    // a new target column closes the open one
             const uint32_t ins_bits = run < ENT_INS_INLINE ? qb << (2 * run) : 0u;
             pend = del ? ENT_VALID : (pend | ins_bits);
             pend_x = del ? x : pend_x; open = true;
@@ -1015,30 +1034,25 @@ k_traceback(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ p
             }
         }
         // snake: interior match columns are plain entries
-        int rem = min(q_len - x, t_len - y);
+        const int rem = min(q_len - x, t_len - y);
         uint32_t diff = win_q(qs + x) ^ win_t(ts + y);
         int adv = min((int)((unsigned)(__ffs(diff) - 1) >> 1), max(min(rem, 16), 0));
-        while (adv > 0 && (adv & 15) == 0 && adv < rem) {            // long snake: rare
+        while (adv > 0 && (adv & 15) == 0 && adv < rem) {                // long snake: rare
             diff = win_q(qs + x + adv) ^ win_t(ts + y + adv);
             const int nn = min((int)((unsigned)(__ffs(diff) - 1) >> 1), min(rem - adv, 16));
             adv += nn;
             if (nn < 16) break;
         }
-        if (adv > 0) {
-            close_pending();
-            int left = adv - 1, xc = x;                              // the last match column stays open
-            while (left > 0) {
-                if ((yo & 3) == 0 && left >= 4) {
-                    if ((yo & 31) == 0) xck[yo >> 5] = (uint32_t)xc;
-                    *reinterpret_cast<uint4*>(ent + yo) = make_uint4(ENT_PLAIN, ENT_PLAIN, ENT_PLAIN, ENT_PLAIN);
-                    yo += 4; xc += 4; left -= 4;
-                } else { emit(ENT_PLAIN, xc); xc++; left--; }
-            }
-            x += adv; y += adv; n_match_cols += adv;
-            pend = ENT_PLAIN; pend_x = x - 1; run = 0; open = true;
-        }
+        const bool snake_on = adv > 0;
+        emit1(snake_on && open, pend | ((uint32_t)run << 22), pend_x);   // the snake's first column closes the open one
+        int left = snake_on ? adv - 1 : 0, xc = x;                       // the last match column stays open
+        for (; left > 16; left -= 16, xc += 16) plain_run(16, xc);       // (only after a long snake)
+        plain_run(left, xc);
+        x += adv; y += adv; n_match_cols += adv;
+        pend = snake_on ? ENT_PLAIN : pend; pend_x = snake_on ? x - 1 : pend_x; run = snake_on ? 0 : run;
+        open = open || snake_on;
     }
-    close_pending();
+    emit1(open, pend | ((uint32_t)run << 22), pend_x);
     {   // the entries of the last, incomplete vector
         const int r = yo & 3, base = yo - r;
         if (r > 0) ent[base] = b0;
