@@ -974,18 +974,22 @@ k_traceback(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ p
     int x = 0, y = 0, run = 0, t_cnt = -1, n_match_cols = 0;
     uint32_t pend = 0; int pend_x = 0; bool open = false;     // entry of the last target column, still open
     uint32_t pw = 0;
-    // x and y creep forward a few bases per step: keep the current two packed words of each
-    // sequence in registers and reload only when the position crosses a word boundary
-    int wq_i = -2, wt_i = -2; uint32_t wq_lo = 0, wq_hi = 0, wt_lo = 0, wt_hi = 0;
+    // x and y creep forward a few bases per step: keep three packed words of each sequence in
+    // registers.  Crossing into the next word shifts the window and issues the load of the word
+    // after next, which is not needed before the following crossing: the load latency stays off
+    // the dependency chain x -> window -> compare -> x.  (Reads are padded: word wi + 2 exists.)
+    int wq_i = -4, wt_i = -4; uint32_t q0 = 0, q1 = 0, q2 = 0, t0 = 0, t1 = 0, t2 = 0;
     auto win_q = [&](const int pos) -> uint32_t {
         const int wi = pos >> 4;
-        if (wi != wq_i) { wq_i = wi; wq_lo = __ldg(q + wi); wq_hi = __ldg(q + wi + 1); }
-        return __funnelshift_r(wq_lo, wq_hi, (pos & 15) << 1);
+        if (wi == wq_i + 1) { q0 = q1; q1 = q2; q2 = __ldg(q + wi + 2); wq_i = wi; }
+        else if (wi != wq_i) { q0 = __ldg(q + wi); q1 = __ldg(q + wi + 1); q2 = __ldg(q + wi + 2); wq_i = wi; }
+        return __funnelshift_r(q0, q1, (pos & 15) << 1);
     };
     auto win_t = [&](const int pos) -> uint32_t {
         const int wi = pos >> 4;
-        if (wi != wt_i) { wt_i = wi; wt_lo = __ldg(t + wi); wt_hi = __ldg(t + wi + 1); }
-        return __funnelshift_r(wt_lo, wt_hi, (pos & 15) << 1);
+        if (wi == wt_i + 1) { t0 = t1; t1 = t2; t2 = __ldg(t + wi + 2); wt_i = wi; }
+        else if (wi != wt_i) { t0 = __ldg(t + wi); t1 = __ldg(t + wi + 1); t2 = __ldg(t + wi + 2); wt_i = wi; }
+        return __funnelshift_r(t0, t1, (pos & 15) << 1);
     };
     // output cursor: yo = number of entries emitted so far (entry yo goes to ent[yo]).  Everything below
     // is straight-line, predicated code: the 32 pairs of a warp take different turns at every step

@@ -78,44 +78,84 @@ k_vote(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, uint32_t n_tiles
         if (n < VCAP) { key[n] = k; cnt[n] = 1; n++; } else overflow = true;
     };
 
-    for (uint32_t j = 0; j < bd.n_pairs; j++) {
-        const VoteMeta vm = vmeta[bd.pair_begin + j];                    // same for the whole CTA
-        if (vm.t_cnt == 0) continue;                                     // pair not accepted
-        if (vm.t_start >= i0 + VOTE_TP || vm.t_start + vm.t_cnt <= i0) continue;   // does not touch this tile
-        const int y = i - vm.t_start;
-        const bool act = in_seed && y >= 0 && y < vm.t_cnt;
-        const uint32_t* ent = ent_arena + vm.ent_off;
-        const uint32_t ec = act ? __ldg(ent + y) : 0u;
+    // The block's reads are taken VOTE_TP at a time: the CTA first lists, in read order, those that are
+    // accepted and touch this tile (one read per thread, ordered compaction), then every thread walks the
+    // list -- a read costs one broadcast LDS.128 instead of a 32-byte descriptor load, range tests and
+    // pointer arithmetic, and reads that do not touch the tile (about half of them) cost nothing.
+    __shared__ uint4 s_list[VOTE_TP];              // {ent pointer lo, hi (biased by -t_start), t_start, t_end}
+    __shared__ uint32_t s_pair[VOTE_TP];           // the pair index, for the rare lookups beyond the inline bases
+    __shared__ uint32_t s_wcnt[VOTE_TP / 32];
+    const unsigned lt = lanemask_lt();
+    for (uint32_t c0 = 0; c0 < bd.n_pairs; c0 += VOTE_TP) {
+        __syncthreads();                           // the previous list is no longer in use
+        const uint32_t jj = c0 + threadIdx.x;
+        bool touch = false; VoteMeta tv; tv.ent_off = 0; tv.t_start = 0; tv.t_cnt = 0;
+        if (jj < bd.n_pairs) {
+            tv = vmeta[bd.pair_begin + jj];
+            touch = tv.t_cnt != 0 && tv.t_start < i0 + VOTE_TP && tv.t_start + tv.t_cnt > i0;
+        }
+        const unsigned tm = __ballot_sync(FULL, touch);
+        if (lane == 0) s_wcnt[threadIdx.x >> 5] = (uint32_t)__popc(tm);
+        __syncthreads();
+        uint32_t at = (uint32_t)__popc(tm & lt), n_list = 0;
+#pragma unroll
+        for (int w = 0; w < VOTE_TP / 32; w++) { const uint32_t c = s_wcnt[w]; if (w < (int)(threadIdx.x >> 5)) at += c; n_list += c; }
+        if (touch) {
+            const uint64_t ep0 = (uint64_t)(ent_arena + tv.ent_off) - (uint64_t)4 * (uint64_t)(int64_t)tv.t_start;   // &ent[0] - t_start: index by i
+            s_list[at] = make_uint4((uint32_t)ep0, (uint32_t)(ep0 >> 32), (uint32_t)tv.t_start, (uint32_t)(tv.t_start + tv.t_cnt));
+            s_pair[at] = jj;
+        }
+        __syncthreads();
+      for (uint32_t li = 0; li < n_list; li++) {
+        const uint4 L = s_list[li];
+        const int t_start = (int)L.z;
+        const bool act = in_seed && i >= t_start && i < (int)L.w;
+        const uint32_t* ent_i = reinterpret_cast<const uint32_t*>(((uint64_t)L.y << 32) | (uint64_t)L.x);   // ent_i[i] = the read's entry at position i
+        const uint32_t ec = act ? __ldg(ent_i + i) : 0u;
         // the read's entry at position i - 1: the left neighbour thread holds it
         uint32_t ep = __shfl_up_sync(FULL, ec, 1);
-        if (lane == 0) ep = (act && y > 0) ? __ldg(ent + y - 1) : 0u;
+        if (lane == 0) ep = (act && i > t_start) ? __ldg(ent_i + i - 1) : 0u;
         if (!act) continue;
         coverage++;
+        const int y = i - t_start;
         const int m = (ec & ENT_MATCH) ? 1 : 0, nins = ent_nins(ec);
         const int b0 = m ? Si : 4;
         // query index at this column: only needed to fetch inserted bases beyond the 11 inline ones
         int x = -1;
-        const uint32_t* qr = pool + vm.q_woff;
         uint32_t pred = LK_START;
         if (y > 0) {
             const int pn = ent_nins(ep);
             int pb;
             if (pn == 0) pb = (ep & ENT_MATCH) ? Sp : 4;
             else if (pn <= ENT_INS_INLINE) pb = ent_ins(ep, pn - 1);
-            else { x = xck_lookup(xck_arena + vm.xck_off, ent, y); pb = base_at(qr, vm.q_s + x - 1); }
+            else {
+                const VoteMeta vm = vmeta[bd.pair_begin + s_pair[li]];
+                x = xck_lookup(xck_arena + vm.xck_off, ent_i + t_start, y); pb = base_at(pool + vm.q_woff, vm.q_s + x - 1);
+            }
             pred = ((uint32_t)pn << 3) | (uint32_t)pb;
         }
         vote(lk_key(0, b0, pred));
         if (nins > 0) {
             maxd = max(maxd, nins);
-            if (nins > ENT_INS_INLINE && x < 0) x = xck_lookup(xck_arena + vm.xck_off, ent, y);
             int pb = b0;
-            for (int lev = 1; lev <= nins; lev++) {
-                const int bb = lev <= ENT_INS_INLINE ? ent_ins(ec, lev - 1) : base_at(qr, vm.q_s + x + m + lev - 1);
-                vote(lk_key(lev, bb, ((uint32_t)(lev - 1) << 3) | (uint32_t)pb));
-                pb = bb;
+            if (nins <= ENT_INS_INLINE) {
+                for (int lev = 1; lev <= nins; lev++) {
+                    const int bb = ent_ins(ec, lev - 1);
+                    vote(lk_key(lev, bb, ((uint32_t)(lev - 1) << 3) | (uint32_t)pb));
+                    pb = bb;
+                }
+            } else {
+                const VoteMeta vm = vmeta[bd.pair_begin + s_pair[li]];
+                if (x < 0) x = xck_lookup(xck_arena + vm.xck_off, ent_i + t_start, y);
+                const uint32_t* qr = pool + vm.q_woff;
+                for (int lev = 1; lev <= nins; lev++) {
+                    const int bb = lev <= ENT_INS_INLINE ? ent_ins(ec, lev - 1) : base_at(qr, vm.q_s + x + m + lev - 1);
+                    vote(lk_key(lev, bb, ((uint32_t)(lev - 1) << 3) | (uint32_t)pb));
+                    pb = bb;
+                }
             }
         }
+      }
     }
     if (!in_seed) return;
     if (idx_dom >= 0) cnt[idx_dom] = c_dom;
