@@ -160,7 +160,7 @@ static thread_local std::string g_create_err;
         }                                                                                 \
     } while (0)
 
-extern "C" const char* fcx_version(void) { return "falcon_b200 0.2 sm_100a"; }
+extern "C" const char* fcx_version(void) { return "falcon_b200 0.3 sm_100a"; }
 
 extern "C" int fcx_device_count(void) {
     int n = 0;

@@ -226,10 +226,21 @@ int fcx_las_take(fcx_dazz *, int seed_cutoff, unsigned min_n_read, unsigned min_
 int fcx_pool_upload_bps(fcx_ctx *, const uint8_t *bps, uint64_t n_bytes, const uint64_t *boff,
                         const int32_t *rlen, uint32_t n_reads);
 
-/* Engine options: "pair_info" (0/1, keep per-pair diagnostics; default 1), "arena_gb" (device
- * memory budget for wave buffers), "max_wave_blocks", "min_wave_blocks", "lanes" (waves in flight,
- * 1..FCX_LANES; with 1 the per-kernel timings of fcx_last_stats are not inflated by overlap),
- * "profile" (0/1). */
+/* Engine options (name, value):
+ *   "pair_info"        0/1  keep the per-pair diagnostics of fcx_last_pair_info (default 1)
+ *   "eqv"              0/1  also produce the eqv array of consensus_data (legacy symbol; default 0)
+ *   "arena_gb"         device-memory budget for the wave buffers, GB (default 85 % of free memory)
+ *   "max_wave_blocks" / "min_wave_blocks"   seed blocks per wave
+ *   "lanes"            waves in flight, 1 .. the number of lanes the engine was created with
+ *                      (environment FCX_LANES at creation, default 3); 0 = all.  With 1 the per-kernel
+ *                      timings of fcx_last_stats are not inflated by overlap
+ *   "dp_variant"       3 = k_dp3 (default: diagonals pinned to lanes, V in registers), 1 = k_dp (round-1
+ *                      kernel, V ring in shared memory), 2 = k_dp with the spans staged by TMA
+ *   "profile"          0/1
+ *   "debug_split_above", "debug_tiny_capacity"   TEST HOOKS: simulate an out-of-memory wave split / start
+ *                      every wave with arenas that are too small (exercises the retry paths)
+ * Environment read at fcx_create: FCX_LANES, FCX_ARENA_GB, FCX_WAVE_BLOCKS, FCX_WAVE_PAIRS, FCX_DP_VARIANT,
+ * FCX_PROFILE, FCX_TRACE_WAVES (per-wave host timeline on stderr). */
 int fcx_set_option(fcx_ctx *, const char *name, double value);
 
 /* Batched banded alignment of sequences of the uploaded pool, distance only: the per-pair call of
@@ -277,12 +288,20 @@ int fcx_multi_consensus_blocks(fcx_multi *, uint32_t n_blocks, const uint32_t *b
 int fcx_multi_last_pair_info(fcx_multi *, fcx_pair_info *out, uint64_t max_pairs, uint64_t *n_pairs);
 int fcx_multi_last_stats(fcx_multi *, double *times_ms, uint64_t *counters);
 
+/* INTERNAL hooks (not part of the supported surface): used by the legacy symbols inside the library
+ * (fcx_legacy.cu) and by tools/profile_run.py. */
+int fcx_internal_want_eqv(fcx_ctx *, int on);
+int fcx_internal_last_eqv(fcx_ctx *, const int32_t **eqv, uint64_t *n);
+int fcx_internal_align(fcx_ctx *, const char *q, int q_len, const char *t, int t_len, int band_tolerance,
+                       int get_aln_str, alignment *out);
+int fcx_internal_profile(fcx_ctx *, double *out8);
+
 /* CUDA-event stopwatch on the engine's stream: start records an event, stop records a second one,
  * waits for it and returns the elapsed device time in milliseconds. */
 int fcx_timer_start(fcx_ctx *);
 int fcx_timer_stop(fcx_ctx *, double *ms);
 
-/* Library identification: returns e.g. "falcon_b200 0.1 sm_100a". */
+/* Library identification: returns "falcon_b200 0.3 sm_100a". */
 const char *fcx_version(void);
 
 #ifdef __cplusplus
