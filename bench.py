@@ -479,7 +479,7 @@ def main():
            "range": SP / 4.0, "index": seed_bases * 4}
     ach = alg.get(dom, 0.0) / (kms[dom] / 1e3) / 1e9 if kms[dom] > 0 else 0.0
     traffic = None
-    kname = {"dp": "k_dp3"}.get(dom, "k_" + dom)
+    kname = {"dp": "k_dp3", "consensus": "k_cns_dp"}.get(dom, "k_" + dom)
     try:   # dram__bytes_read+write per launch of the dominant kernel, from the committed ncu capture
         prof = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))
         k = prof.get(kname)

@@ -83,6 +83,14 @@ def main():
             for a, b in m.items():
                 lines.append("* `%s` = %s %s\n" % (a, b[0], b[1]))
             lines.append("* top stall reasons (%% of samples): %s\n" % ", ".join("%s %.1f" % x for x in st))
+    # compute-sanitizer logs of the same session (tools/sanitize_run.py)
+    for tool in ("memcheck", "racecheck"):
+        fn = os.path.join(OUT, "sanitize_%s.log" % tool)
+        if os.path.exists(fn):
+            txt = open(fn, errors="replace").read().splitlines()
+            keep = [l for l in txt if "ERROR SUMMARY" in l or "SANITIZE RUN" in l or l.startswith(tool + " rc=") or "RACECHECK SUMMARY" in l]
+            lines.append("\n## compute-sanitizer --tool %s (python tools/sanitize_run.py)\n\n" % tool)
+            lines.extend("* `%s`\n" % l.strip() for l in keep[-6:])
     # pairs in the profiled launch (from the log of the launch-list run)
     log = os.path.join(OUT, "launches.log")
     pairs = None
