@@ -337,8 +337,19 @@ def main():
         # views of the engine's result buffers (host memory): the step's output, no extra Python copy
         return eng.consensus_blocks_raw(block_off, ids, args.min_cov, args.min_idt, copy=False)
 
+    _gbuf = {}
+
+    def _cached(name, n, dtype, **kw):
+        t = _gbuf.get(name)
+        if t is None or t.numel() < n:
+            t = torch.empty(max(n, 1), dtype=dtype, **kw)
+            _gbuf[name] = t
+        return t
+
     def gather_to_rank0(data, off):
-        """Consensus bytes + lengths of every rank -> rank 0, merged in seed order."""
+        """Consensus bytes + lengths of every rank -> rank 0, merged in seed order (slices are contiguous in
+        seed order, so the merge is a concatenation): NCCL gather of the padded byte buffers, then rank 0
+        copies each rank's part straight into place in ONE pinned host buffer."""
         if world == 1:
             return data, off
         lens = np.diff(off).astype(np.int64)
@@ -347,21 +358,31 @@ def main():
         dist.all_gather(allsz, sizes)
         allsz = [t.tolist() for t in allsz]
         mx_d, mx_l = max(s[0] for s in allsz), max(s[1] for s in allsz)
-        td = torch.zeros(mx_d, dtype=torch.uint8, device=dev)
-        td[:data.shape[0]] = torch.from_numpy(data).to(dev)
-        tl = torch.zeros(mx_l, dtype=torch.int64, device=dev)
-        tl[:lens.shape[0]] = torch.from_numpy(lens).to(dev)
-        gd = [torch.empty(mx_d, dtype=torch.uint8, device=dev) for _ in range(world)] if rank == 0 else None
-        gl = [torch.empty(mx_l, dtype=torch.int64, device=dev) for _ in range(world)] if rank == 0 else None
+        td = _cached("td", mx_d, torch.uint8, device=dev)[:mx_d]
+        td[:data.shape[0]].copy_(torch.from_numpy(data))
+        tl = _cached("tl", mx_l, torch.int64, device=dev)[:mx_l]
+        tl[:lens.shape[0]].copy_(torch.from_numpy(lens))
+        gd = gl = None
+        if rank == 0:
+            gd = [_cached("gd%d" % k, mx_d, torch.uint8, device=dev)[:mx_d] for k in range(world)]
+            gl = [_cached("gl%d" % k, mx_l, torch.int64, device=dev)[:mx_l] for k in range(world)]
         dist.gather(td, gd, dst=0)
         dist.gather(tl, gl, dst=0)
         if rank != 0:
             return None, None
-        datas = [gd[k][:allsz[k][0]].cpu().numpy() for k in range(world)]          # slices are contiguous in
-        lens_all = np.concatenate([gl[k][:allsz[k][1]].cpu().numpy() for k in range(world)])   # seed order
-        moff = np.zeros(lens_all.shape[0] + 1, dtype=np.uint64)
-        np.cumsum(lens_all, out=moff[1:])
-        return np.concatenate(datas), moff
+        tot_d, tot_l = sum(s[0] for s in allsz), sum(s[1] for s in allsz)
+        out_d = _cached("out_d", tot_d, torch.uint8, pin_memory=True)[:tot_d]
+        out_l = _cached("out_l", tot_l, torch.int64, pin_memory=True)[:tot_l]
+        od = ol = 0
+        for k in range(world):
+            nd, nl = allsz[k]
+            out_d[od:od + nd].copy_(gd[k][:nd], non_blocking=True)
+            out_l[ol:ol + nl].copy_(gl[k][:nl], non_blocking=True)
+            od += nd; ol += nl
+        torch.cuda.synchronize()
+        moff = np.zeros(tot_l + 1, dtype=np.uint64)
+        np.cumsum(out_l.numpy(), out=moff[1:])
+        return out_d.numpy(), moff
 
     def timed(fn, steps):
         barrier()
