@@ -58,7 +58,7 @@ __device__ __forceinline__ int dp3_snake16(const uint32_t* __restrict__ q, const
 __global__ void __launch_bounds__(DP3_WARPS * 32)
 k_dp3(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs,
       const PairRange* __restrict__ ranges, const PairAlloc* __restrict__ allocs, uint32_t n_pairs,
-      const uint32_t* __restrict__ pool, uint32_t* trace_arena, uint32_t* __restrict__ path_arena, double max_diff,
+      const uint32_t* __restrict__ pool, uint32_t* trace_arena, uint32_t trace_stride, uint32_t* __restrict__ path_arena, double max_diff,
       uint32_t* __restrict__ next_pair, PairAln* __restrict__ out) {
     __shared__ int s_V[DP3_WARPS][VRING];          // wide mode only
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -85,7 +85,10 @@ k_dp3(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs,
     asm volatile("" : "+l"(t));         // re-deriving pool + offset for every load
 #endif
     const PairAlloc al = allocs[p];
-    uint32_t* trace = trace_arena + al.trace_off * TRACE_REC_WORDS;
+    // The trace of a pair is dead as soon as this warp has walked it backwards (below), so it lives in a
+    // scratch area owned by the WARP (trace_stride records), reused pair after pair: the trace memory of a
+    // wave is (resident warps) x (longest trace), not the sum over all pairs, and mostly stays in L2.
+    uint32_t* trace = trace_arena + (size_t)(blockIdx.x * DP3_WARPS + wib) * trace_stride * TRACE_REC_WORDS;
     const int trace_cap = (int)al.trace_cap;
     const int store_cap = lane == 0 ? trace_cap : 0;           // lane 0 writes the trace records
     const int lane_up = (lane + 1) & 31, lane_dn = (lane + 31) & 31;

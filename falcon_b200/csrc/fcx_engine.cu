@@ -551,7 +551,7 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
     tl[3] = now_ms();
     // ---- exact per-pair allocations
     std::vector<PairAlloc> ha(np);
-    uint64_t trace_recs = 0, xam_n = 0, xck_n = 0, path_w = 0, dp_pairs = 0, span_bases = 0; uint32_t max_span = 0;
+    uint64_t trace_recs = 0, xam_n = 0, xck_n = 0, path_w = 0, dp_pairs = 0, span_bases = 0; uint32_t max_span = 0, max_trace_cap = 1;
     const PairRange* hr = L.h_ranges.as<PairRange>();
     for (uint32_t p = 0; p < np; p++) {
         ha[p].trace_off = trace_recs; ha[p].xam_off = xam_n; ha[p].path_off = path_w; ha[p].trace_cap = 0; ha[p].xck_off = (uint32_t)xck_n;
@@ -564,12 +564,16 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
             uint64_t md = max_d_of(ql, tl);
             if (mdiff < 1.999) md = std::min<uint64_t>(md, (uint64_t)(mdiff * (ql + tl) / (2.0 - mdiff)) + 2);
             ha[p].trace_cap = (uint32_t)(md + 1);
+            max_trace_cap = std::max(max_trace_cap, (uint32_t)(md + 1));
             trace_recs += md + 1; xam_n += ((uint64_t)tl + 4 + 3) & ~(uint64_t)3; xck_n += (uint64_t)tl / 32 + 2; path_w += md / 32 + 2;
             dp_pairs++; span_bases += (uint64_t)ql + tl;
             max_span = std::max(max_span, (uint32_t)std::max(ql, tl));
         }
     }
-    CKR(L.d_trace.reserve(trace_recs * TRACE_REC_WORDS * 4 + 64));
+    // k_dp3 walks every trace back inside the DP warp: one scratch trace per resident warp instead of one per pair
+    const unsigned dp_grid = std::min<unsigned>((np + DP3_WARPS - 1) / DP3_WARPS, (unsigned)ctx->sm_count * 32u);
+    if (ctx->dp_variant == 3) CKR(L.d_trace.reserve((size_t)std::max(dp_grid, 1u) * DP3_WARPS * max_trace_cap * TRACE_REC_WORDS * 4 + 64));
+    else CKR(L.d_trace.reserve(trace_recs * TRACE_REC_WORDS * 4 + 64));
     if (xck_n > 0xffffffffull) { L.err = "out of device memory (checkpoint index)"; return 100; }    // split the wave
     CKR(L.d_xam.reserve(xck_n * 4 + 128));
     CKR(L.d_ent.reserve(xam_n * 4 + 128));
@@ -583,10 +587,9 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
             // default: one warp per pair, diagonals pinned to lanes, V in registers (fcx_dp.cuh)
             CKR(L.d_counter.reserve(64));
             CKL(cudaMemsetAsync(L.d_counter.p, 0, 64, st));
-            const unsigned dp_grid = std::min<unsigned>((np + DP3_WARPS - 1) / DP3_WARPS, (unsigned)ctx->sm_count * 32u);
             FCX_LAUNCH(k_dp3, dp_grid, DP3_WARPS * 32, 0, st,
                        L.d_blocks.as<BlockDesc>(), L.d_pairs.as<PairDesc>(), L.d_ranges.as<PairRange>(),
-                       L.d_allocs.as<PairAlloc>(), np, pool, L.d_trace.as<uint32_t>(), L.d_path.as<uint32_t>(), 1.0 - min_idt,
+                       L.d_allocs.as<PairAlloc>(), np, pool, L.d_trace.as<uint32_t>(), max_trace_cap, L.d_path.as<uint32_t>(), 1.0 - min_idt,
                        L.d_counter.as<uint32_t>(), L.d_aln.as<PairAln>());
         } else {
             // round-1 kernels kept for A/B measurement: shared-memory V ring, lanes re-mapped to the
@@ -772,7 +775,16 @@ extern "C" int fcx_consensus_blocks(fcx_ctx* ctx, uint32_t n_blocks, const uint3
     uint32_t target = (n_blocks + n_waves - 1) / std::max(1u, n_waves);
     target = std::max(target, ctx->min_wave_blocks);
     target = std::min(target, ctx->max_wave_blocks);
-    const double budget = (double)ctx->arena_budget / nl;
+    double budget = (double)ctx->arena_budget / nl;
+    if (ctx->dp_variant == 3) {              // k_dp3's trace scratch: (resident warps) x (longest trace of the call, upper bound)
+        int max_s = 1, max_r = 1;
+        for (uint32_t b = 0; b < n_blocks; b++) {
+            max_s = std::max(max_s, ctx->h_len[read_ids[block_off[b]]]);
+            for (uint32_t i = block_off[b] + 1; i < block_off[b + 1]; i++) max_r = std::max(max_r, ctx->h_len[read_ids[i]]);
+        }
+        budget -= (double)ctx->sm_count * 32 * DP3_WARPS * (0.3 * ((double)max_s + max_r) + 2) * TRACE_REC_WORDS * 4;
+        budget = std::max(budget, 1e9);
+    }
     std::vector<std::pair<uint32_t, uint32_t>> waves;
     auto pack = [&](uint32_t tgt) {
         waves.clear();
@@ -788,7 +800,7 @@ extern "C" int fcx_consensus_blocks(fcx_ctx* ctx, uint32_t n_blocks, const uint3
                     // typical aligned span ~ 0.65 x the shorter sequence (exact sizes follow k_range;
                     // an under-estimate is caught by the out-of-memory split below)
                     const double span = 0.65 * std::min(ctx->h_len[read_ids[i]], slen);
-                    bb += capfrac * 2.0 * span * 33.0 + 4.0 * (span + 8) + 128;
+                    bb += (ctx->dp_variant == 3 ? 0.0 : capfrac * 2.0 * span * 33.0) + 4.0 * (span + 8) + 128;      // (k_dp3: per-warp trace scratch, below)
                 }
                 if (e > b && (bytes + bb > budget || pairs + (hi - lo - 1) > ctx->max_wave_pairs || e - b >= tgt)) break;
                 bytes += bb; pairs += hi - lo - 1; e++;

@@ -283,7 +283,10 @@ __device__ FCX_NOINLINE void cdp_position_slow(CdpState& S, const int lane, cons
     if (lev >= 0) close_level();
 }
 
-__global__ void __launch_bounds__(CDP_WARPS * 32, 5)
+#ifndef CDP_MIN_CTAS
+#define CDP_MIN_CTAS 5
+#endif
+__global__ void __launch_bounds__(CDP_WARPS * 32, CDP_MIN_CTAS)
 k_cns_dp(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, const VoteMeta* __restrict__ vmeta,
          const uint2* __restrict__ slot_arena, const uint2* __restrict__ ovf_arena,
          CnsRec* __restrict__ rec_arena, int32_t* __restrict__ lvl_scratch,
