@@ -186,6 +186,8 @@ def main():
     ap.add_argument("--genome", type=int, default=0, help="genome size (0 = 4.6 Mb at N=1, 36.8 Mb at N>=2)")
     ap.add_argument("--read-len", type=int, default=15000)
     ap.add_argument("--cov", type=float, default=50.0)
+    ap.add_argument("--ploidy", type=int, default=1, choices=[1, 2], help="2: diploid set, two haplotypes with --het SNPs (BASELINE config 5)")
+    ap.add_argument("--het", type=float, default=0.01)
     ap.add_argument("--blocks", type=int, default=0, help="seed blocks per step (0 = every read is a seed)")
     ap.add_argument("--max-n-read", type=int, default=200)
     ap.add_argument("--min-cov", type=int, default=4)
@@ -202,6 +204,8 @@ def main():
     genome = args.genome or (ECOLI if world == 1 else 8 * ECOLI)
     cores = usable_cores()
     name = "E. coli-like" if genome <= 5_000_000 else "D. mel-like slice"
+    if args.ploidy == 2:
+        name = "diploid (%g %% het)" % (100 * args.het)
     workload = ("synthetic %s %.1f Mb, %gx %d kb reads, 15%% error (ins 9/del 4.5/sub 1.5); %s seed blocks per step, "
                 "max_n_read %d; ONE data set sharded over %d GPU(s)" %
                 (name, genome / 1e6, args.cov, args.read_len // 1000, args.blocks or "all", args.max_n_read, world))
@@ -213,7 +217,7 @@ def main():
     scaling = "strong" if world > 1 else "weak"   # N=1 has nothing to scale; N>=2 share one fixed data set
 
     from falcon_b200 import synth, shard
-    geo = synth.make_geometry(genome, args.read_len, args.cov, seed=args.seed)
+    geo = synth.make_geometry(genome, args.read_len, args.cov, seed=args.seed, ploidy=args.ploidy, het=args.het)
     n_reads = geo.n_reads
 
     # ---------------------------------------------------------------- reference arm
@@ -282,12 +286,23 @@ def main():
     cuts = [n_reads * r // world for r in range(world + 1)]
     r0, r1 = cuts[rank], cuts[rank + 1]
     t_gen = time.perf_counter()
-    part = synth.gen_reads(geo, r0, r1)                                   # 2 pool entries per read
-    plen = np.fromiter((len(x) for x in part), dtype=np.uint64, count=len(part))
-    poff = np.zeros(len(part) + 1, dtype=np.uint64)
+    # generated 512 reads at a time straight into the pinned buffer (2 pool entries per read): at the 1 Gb
+    # configuration a rank's part is ~8 GB and must not exist three times on the host
+    n_part = 2 * (r1 - r0)
+    cap = int(2 * float(geo.lens[r0:r1].sum()) * (1.0 + geo.p_ins + 0.03)) + (1 << 20)
+    pbuf = PinnedBuffer(cap)
+    plen = np.zeros(n_part, dtype=np.uint64)
+    at = 0
+    for a in range(r0, r1, 512):
+        chunk = synth.gen_reads(geo, a, min(r1, a + 512))
+        blob = b"".join(chunk)
+        if at + len(blob) > cap:
+            raise RuntimeError("bench.py: pinned read buffer too small (raise the slack)")
+        pbuf.array[at:at + len(blob)] = np.frombuffer(blob, dtype=np.uint8)
+        plen[2 * (a - r0):2 * (a - r0) + len(chunk)] = [len(x) for x in chunk]
+        at += len(blob)
+    poff = np.zeros(n_part + 1, dtype=np.uint64)
     np.cumsum(plen, out=poff[1:])
-    pbuf = PinnedBuffer(int(poff[-1]))
-    pbuf.array[:int(poff[-1])] = np.frombuffer(b"".join(part), dtype=np.uint8)
     # lengths of all pool entries (tiny all-gather: the layout must be the same everywhere)
     noisy = np.zeros(n_reads, dtype=np.int64)
     noisy[r0:r1] = plen[0::2].astype(np.int64)
@@ -452,7 +467,11 @@ def main():
             if not (r0 <= r < r1):
                 g = synth.gen_reads(geo, r, r + 1)
                 extra[2 * r], extra[2 * r + 1] = g[0], g[1]
-        reads = lambda i: part[i - 2 * r0] if 2 * r0 <= i < 2 * r1 else extra[i]      # noqa: E731
+        def reads(i):
+            if 2 * r0 <= i < 2 * r1:
+                j = i - 2 * r0
+                return pbuf.array[int(poff[j]):int(poff[j + 1])].tobytes()
+            return extra[i]
         jobs = [([reads(int(i)) for i in blocks[b]], args.min_cov, args.min_idt) for b in sids]
         pairs = sum(len(j[0]) - 1 for j in jobs)
         cpu = CpuReference(cores)

@@ -102,6 +102,8 @@ class Geometry:
     p_ins: float
     p_del: float
     p_sub: float
+    genome_b: Optional[np.ndarray] = None      # second haplotype (diploid sets): read r comes from haplotype hap[r]
+    hap: Optional[np.ndarray] = None
 
     @property
     def n_reads(self) -> int:
@@ -110,7 +112,10 @@ class Geometry:
 
 def make_geometry(genome_size: int, read_len: int, coverage: float, seed: int = 20260924,
                   len_sigma: float = 0.0, p_ins: float = 0.09, p_del: float = 0.045,
-                  p_sub: float = 0.015) -> Geometry:
+                  p_sub: float = 0.015, ploidy: int = 1, het: float = 0.01) -> Geometry:
+    """``ploidy`` 2: two haplotypes differing by ``het`` SNPs (BASELINE config 5); ``coverage`` is the
+    total over both, every read is drawn from one haplotype, seed blocks are built from positional
+    overlap regardless of haplotype (what an overlapper would report at 1 % divergence)."""
     rng = np.random.default_rng(seed)
     genome = random_codes(genome_size, rng)
     n_reads = max(2, int(round(genome_size * coverage / read_len)))
@@ -124,7 +129,16 @@ def make_geometry(genome_size: int, read_len: int, coverage: float, seed: int = 
     order = np.argsort(starts, kind="stable")
     starts, lens = starts[order], lens[order]
     strands = rng.integers(0, 2, n_reads)
-    return Geometry(genome, starts, lens, starts + lens, strands, seed, p_ins, p_del, p_sub)
+    genome_b = hap = None
+    if ploidy == 2:
+        rng_b = np.random.default_rng([seed, 0x68617062])
+        genome_b = genome.copy()
+        for c0 in range(0, genome_size, 1 << 26):                 # in pieces: a 1 Gb genome must not need 8 GB of doubles
+            c1 = min(genome_size, c0 + (1 << 26))
+            snp = c0 + np.flatnonzero(rng_b.random(c1 - c0) < het)
+            genome_b[snp] = (genome_b[snp] + rng_b.integers(1, 4, snp.shape[0]).astype(genome_b.dtype)) & 3
+        hap = rng_b.integers(0, 2, n_reads)
+    return Geometry(genome, starts, lens, starts + lens, strands, seed, p_ins, p_del, p_sub, genome_b, hap)
 
 
 def gen_reads(geo: Geometry, r0: int, r1: int) -> List[bytes]:
@@ -134,7 +148,8 @@ def gen_reads(geo: Geometry, r0: int, r1: int) -> List[bytes]:
     out: List[bytes] = []
     for r in range(r0, r1):
         rng = np.random.default_rng([geo.seed, r])
-        fwd = add_errors(geo.genome[geo.starts[r]:geo.ends[r]], rng, geo.p_ins, geo.p_del, geo.p_sub)
+        g = geo.genome_b if (geo.hap is not None and geo.hap[r]) else geo.genome
+        fwd = add_errors(g[geo.starts[r]:geo.ends[r]], rng, geo.p_ins, geo.p_del, geo.p_sub)
         if fwd.shape[0] > 99998:
             fwd = fwd[:99998]
         out.append(codes_to_bytes(fwd))
