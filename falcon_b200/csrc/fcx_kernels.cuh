@@ -1,15 +1,20 @@
 // fcx_kernels.cuh -- device code of the B200-native fc_consensus engine (sm_100a).
 //
-// Pipeline per wave of seed blocks (all integer work, HBM/latency bound, no tensor cores):
-//   k_pack       ASCII -> 2-bit packed reads (A0 C1 G2 T3, 16 bases / 32-bit word, LSB first)
+// Pipeline per wave of seed blocks (all integer work, issue/latency bound, no tensor cores):
+//   k_pack / k_repack_bps / k_subreads   the 2-bit packed read pool (A0 C1 G2 T3, 16 bases / 32-bit word,
+//                LSB first) from ASCII, from a Dazzler .bps image, or cut out of packed reads (--trim)
 //   k_index      per seed: K=8 k-mer CSR index           (ref: src/c/kmer_lookup.c:140-192)
 //   k_range      per pair: k-mer hits + best range        (ref: kmer_lookup.c:207-286, 294-427,
 //                                                               falcon.c:612-619)
-//   k_dp         per pair: banded O(ND) forward pass      (ref: src/c/DW_banded.c:115-258)
-//   k_traceback  per pair: path walk + forward replay     (ref: DW_banded.c:260-320,
-//                                                               falcon.c:106-162)
-//   k_consensus  per block: column vote, link-DAG longest path, backtrack
-//                                                         (ref: falcon.c:308-558)
+//   k_dp3        per pair: banded O(ND) forward pass + backward walk of the trace   (fcx_dp.cuh;
+//                                                          ref: src/c/DW_banded.c:115-277)
+//   k_traceback  per pair: forward replay of the path -> per-column entries
+//                                                         (ref: DW_banded.c:284-320, falcon.c:106-162)
+//   k_vote       per seed position: column vote          (fcx_vote.cuh; ref: falcon.c:350-382)
+//   k_cns_dp     per block: link-DAG longest path, backtrack   (fcx_vote.cuh; ref: falcon.c:405-542)
+//   k_trim_range per pair: masked k-mer hits + find_best_aln_range2   (fcx_trim.cuh; --trim)
+//   k_dp<>, k_traceback_walk   the round-1 DP kernels (A/B: dp_variant 1 / 2, the latter TMA-staged)
+//   k_align1 / k_align1_tb / k_align_batch   align() with an arbitrary band (legacy symbol, stage 2)
 //
 // Every kernel reproduces the reference's integer/double semantics exactly, including the quirks
 // listed in SURVEY.md 8(a)-notes; see DESIGN.md for the data layout.
@@ -1077,12 +1082,6 @@ __device__ __forceinline__ int xck_lookup(const uint32_t* __restrict__ xck, cons
     int x = (int)xck[y >> 5];
     for (int j = y & ~31; j < y; j++) { const uint32_t e = ent[j]; x += ((e & ENT_MATCH) ? 1 : 0) + ent_nins(e); }
     return x;
-}
-
-// ------------------------------------------------------------------------------ k_fill32
-__global__ void k_fill32(uint4* __restrict__ dst, uint64_t n16, uint32_t v) {
-    const uint4 val = make_uint4(v, v, v, v);
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (uint64_t)gridDim.x * blockDim.x) dst[i] = val;
 }
 
 // ------------------------------------------------------------------------------ k_align1 / k_align1_tb

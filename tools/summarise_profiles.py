@@ -45,7 +45,7 @@ def main():
     os.makedirs(PROF, exist_ok=True)
     summary = {}
     lines = ["# ncu summaries (%s)\n" % tag,
-             "Command: `python tools/profile_run.py --blocks 2960 --reps 1` (one full wave, FCX_LANES=1), see tools/capture_profiles.sh.\n"]
+             "Command: `python tools/profile_run.py --blocks 2960 --reps 1` (one full wave, FCX_LANES=1), see tools/gpu_round2_final1.sh.\n"]
     # launch list
     src = os.path.join(OUT, "launches.csv")
     if os.path.exists(src):
