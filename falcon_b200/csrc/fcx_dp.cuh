@@ -47,12 +47,13 @@ __device__ __forceinline__ uint32_t dp3_fetch(const uint32_t* __restrict__ w, in
 // advance: n == rem means an end was reached (DW_banded.c:220), n == 16 < rem that the snake goes
 // on (:203-206).
 __device__ __forceinline__ int dp3_snake16(const uint32_t* __restrict__ q, const uint32_t* __restrict__ t,
-                                           int qe, int te, int X, int kk, int& rem) {
+                                           int qe, int te, int X, int kk, int& rem, unsigned& lim) {
     const int Y = X - kk;
     rem = min(qe - X, te - Y);
     const uint32_t diff = dp3_fetch(q, X) ^ dp3_fetch(t, Y);
     const unsigned run = (unsigned)(__ffs(diff) - 1) >> 1;      // diff == 0 -> 0x7fffffff
-    return (int)min(min(run, 16u), (unsigned)rem);
+    lim = min(16u, (unsigned)rem);                              // n == lim: an end reached, or 16 matches and more to compare
+    return (int)min(run, lim);
 }
 
 __global__ void __launch_bounds__(DP3_WARPS * 32)
@@ -105,7 +106,7 @@ k_dp3(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs,
         if (lane == 0 && trace_cap > 0) { trace[0] = 0u; trace[1] = 1u; }
         cells = 1;
         if (x >= q_len || y >= t_len) { aligned = true; end_x = x; end_y = y; }
-        else { Va = qs + x; best = qs + x + ts + y; lo = -1; ncell = 2; }   // d = 1: k = -1, +1 -> m = -1, 0
+        else { Va = Vb = qs + x; best = qs + x + ts + y; lo = -1; ncell = 2; }   // d = 1: k = -1, +1 -> m = -1, 0
     }
 
     // ------------------------------------------------------------------ register-resident steps
@@ -121,7 +122,9 @@ k_dp3(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs,
         cells += ncell;                                         // (corrected on an early exit)
         const int c0 = (lane - lo) & 31;                        // band index of my first cell
         const int m0 = lo + c0;
-        const bool s0 = (m0 & 32) != 0;
+        // One-cell steps keep the lane's single value in BOTH slots (see the write-back), so they need no
+        // slot selection; a two-cell step that follows finds the value in whichever slot it looks.
+        const bool s0 = TWO && (m0 & 32) != 0;
         const int W0 = s0 ? Vb : Va;                            // prev[m0]
         const int W1 = s0 ? Va : Vb;                            // prev[m0 + 32] (TWO only)
         int nb0, nb1 = 0;                                       // the neighbours held by other lanes
@@ -130,32 +133,37 @@ k_dp3(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs,
         else { nb0 = __shfl_sync(FULL, W0, lane_dn); nb1 = __shfl_sync(FULL, c0 == 31 ? W0 : W1, lane_dn); }
         // predecessor choice, DW_banded.c:190-197: min_k takes k+1, max_k takes k-1, ties take k-1
         const int vm0 = P ? W0 : nb0, vp0 = P ? nb0 : W0;
+        // (the edge rules as value substitutions: X = max(V[k+1], V[k-1] + 1) with the missing side at -inf;
+        //  ties vm == vp - 1 ... the reference takes k+1 iff V[k-1] < V[k+1], and then V[k+1] >= V[k-1] + 1)
         const bool act0 = TWO || c0 <= last;
-        const bool up0 = c0 == 0 || (c0 != last && vm0 < vp0);
-        int X0 = up0 ? vp0 : vm0 + 1;
+        const int vmx0 = c0 == 0 ? INT_MIN : vm0, vpx0 = c0 == last ? INT_MIN : vp0;
+        const bool up0 = vmx0 < vpx0;
+        int X0 = max(vpx0, vmx0 + 1);
         int kk0 = 2 * m0 + (P - dts);
         if (!act0) { X0 = qe; kk0 = qe - te; }                  // parked on the span ends: rem = 0, n = 0
         int rem0, rem1 = 0, n1 = 0, X1 = 0, kk1 = 0;
+        unsigned lim0, lim1 = 1u;
         bool act1 = false, up1 = false;
-        int n0 = dp3_snake16(q, t, qe, te, X0, kk0, rem0);
+        int n0 = dp3_snake16(q, t, qe, te, X0, kk0, rem0, lim0);
         X0 += n0;
         if (TWO) {
             const int vm1 = P ? W1 : nb1, vp1 = P ? nb1 : W1;
             act1 = c0 + 32 <= last;
-            up1 = c0 + 32 != last && vm1 < vp1;
-            X1 = up1 ? vp1 : vm1 + 1;
+            const int vpx1 = c0 + 32 == last ? INT_MIN : vp1;
+            up1 = vm1 < vpx1;
+            X1 = max(vpx1, vm1 + 1);
             kk1 = kk0 + 64;
             if (!act1) { X1 = qe; kk1 = qe - te; }
-            n1 = dp3_snake16(q, t, qe, te, X1, kk1, rem1);
+            n1 = dp3_snake16(q, t, qe, te, X1, kk1, rem1, lim1);
             X1 += n1;
         }
         // rare: a snake longer than 16 bases, or an end reached
-        bool fin0 = act0 && n0 == rem0, fin1 = TWO && act1 && n1 == rem1;
-        if (__any_sync(FULL, n0 == 16 || fin0 || (TWO && (n1 == 16 || fin1)))) {
-            bool g0 = n0 == 16 && !fin0, g1 = TWO && n1 == 16 && !fin1;
+        if (__any_sync(FULL, (act0 && (unsigned)n0 == lim0) || (TWO && act1 && (unsigned)n1 == lim1))) {
+            bool fin0 = act0 && n0 == rem0, fin1 = TWO && act1 && n1 == rem1;
+            bool g0 = act0 && n0 == 16 && !fin0, g1 = TWO && act1 && n1 == 16 && !fin1;
             while (__any_sync(FULL, g0 || g1)) {
-                if (g0) { n0 = dp3_snake16(q, t, qe, te, X0, kk0, rem0); X0 += n0; fin0 = n0 == rem0; g0 = n0 == 16 && !fin0; }
-                if (g1) { n1 = dp3_snake16(q, t, qe, te, X1, kk1, rem1); X1 += n1; fin1 = n1 == rem1; g1 = n1 == 16 && !fin1; }
+                if (g0) { n0 = dp3_snake16(q, t, qe, te, X0, kk0, rem0, lim0); X0 += n0; fin0 = n0 == rem0; g0 = n0 == 16 && !fin0; }
+                if (g1) { n1 = dp3_snake16(q, t, qe, te, X1, kk1, rem1, lim1); X1 += n1; fin1 = n1 == rem1; g1 = n1 == 16 && !fin1; }
             }
             const unsigned f0 = rot_band(__ballot_sync(FULL, fin0), lo);
             const unsigned f1 = TWO ? rot_band(__ballot_sync(FULL, fin1), lo) : 0u;
@@ -183,9 +191,9 @@ k_dp3(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs,
             const unsigned upb1 = rot_band(__ballot_sync(FULL, up1), lo);
             if (d < store_cap) trace[(size_t)d * TRACE_REC_WORDS + 2] = upb1;
         }
-        // write back: the slot of m0 gets X0, the other slot X1
-        if (s0) Vb = X0; else Va = X0;
-        if (TWO) { if (s0) Va = X1; else Vb = X1; }
+        // write back: the slot of m0 gets X0, the other slot X1 -- or X0 too in a one-cell step
+        if (TWO) { if (s0) { Vb = X0; Va = X1; } else { Va = X0; Vb = X1; } }
+        else { Va = X0; Vb = X0; }
         // band update, DW_banded.c:227-243.  u = X + Y (biased); parked lanes are excluded
         const int u0 = act0 ? 2 * X0 - kk0 : INT_MIN;
         const int u1 = TWO ? (act1 ? 2 * X1 - kk1 : INT_MIN) : INT_MIN;
@@ -200,6 +208,13 @@ k_dp3(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs,
         } else { cmin = __ffs(okb0) - 1; cmax = 31 - __clz(okb0); }
         lo = lo + cmin - 1 + P;                                 // min_k' = nmin - 1 on the other parity
         ncell = cmax - cmin + 2;                                // max_k' = nmax + 1
+        if (TWO && ncell <= 31) {
+            // the next step has one cell per lane and reads Va only: every lane keeps the value of the
+            // diagonal it owns in the narrower band (in both slots)
+            const int mn = lo + ((lane - lo) & 31);
+            const int v = (mn & 32) ? Vb : Va;
+            Va = v; Vb = v;
+        }
         return 0;
     };
     using I0 = std::integral_constant<int, 0>;
