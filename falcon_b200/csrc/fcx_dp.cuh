@@ -110,16 +110,21 @@ k_dp3(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs,
     }
 
     // ------------------------------------------------------------------ register-resident steps
-    // One step of parity P with one (TWO = 0: <= 31 cells) or two cells per lane.  The four variants
+    // One step of parity P with one (TWO = 0: <= 32 cells) or two cells per lane.  The four variants
     // are separate straight-line bodies so that the common one-cell step carries no moves or
     // predicates of the two-cell case.  Returns 0: go on, 1: aligned.
-    // A second cell per lane is needed from 32 cells on, because the cell with band index 31 reads
-    // a neighbour from the SECOND slot of the lane that holds band index 0.
+    // A second cell per lane is needed from 33 cells on: with 32 cells every lane owns exactly one
+    // diagonal, and the two band edges, whose outer neighbours would alias onto the opposite edge's lane,
+    // never read them (min_k takes k+1, max_k takes k-1).
     auto step = [&](auto PC, auto TC) -> int {
         constexpr int P = decltype(PC)::value;
         constexpr bool TWO = decltype(TC)::value != 0;
         const int last = ncell - 1;
         cells += ncell;                                         // (corrected on an early exit)
+#ifdef FCX_EMU
+        if (lane == 0) { static long hist[80]; static bool reg = false; hist[ncell < 79 ? ncell : 79]++;
+            if (!reg && getenv("FCX_EMU_NCELL_HIST")) { reg = true; atexit([] { for (int i = 0; i < 80; i++) if (hist[i]) fprintf(stderr, "ncell %d: %ld\n", i, hist[i]); }); } }
+#endif
         const int c0 = (lane - lo) & 31;                        // band index of my first cell
         const int m0 = lo + c0;
         // One-cell steps keep the lane's single value in BOTH slots (see the write-back), so they need no
@@ -208,7 +213,7 @@ k_dp3(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs,
         } else { cmin = __ffs(okb0) - 1; cmax = 31 - __clz(okb0); }
         lo = lo + cmin - 1 + P;                                 // min_k' = nmin - 1 on the other parity
         ncell = cmax - cmin + 2;                                // max_k' = nmax + 1
-        if (TWO && ncell <= 31) {
+        if (TWO && ncell <= 32) {
             // the next step has one cell per lane and reads Va only: every lane keeps the value of the
             // diagonal it owns in the narrower band (in both slots)
             const int mn = lo + ((lane - lo) & 31);
@@ -223,12 +228,12 @@ k_dp3(const BlockDesc* __restrict__ blocks, const PairDesc* __restrict__ pairs,
     if (status == 0) {
         for (;;) {                              // d is odd at the top: the parity is static in each half
             if (d >= max_d) break;
-            if (ncell > 31) { if (ncell > 64) { status = 2; break; } status = step(I1(), I1()); }   // > 64: wide mode
+            if (ncell > 32) { if (ncell > 64) { status = 2; break; } status = step(I1(), I1()); }   // > 64: wide mode
             else status = step(I1(), I0());                                                          //   (or > 151: abort, :184)
             if (status) break;
             d++;
             if (d >= max_d) break;
-            if (ncell > 31) { if (ncell > 64) { status = 2; break; } status = step(I0(), I1()); }
+            if (ncell > 32) { if (ncell > 64) { status = 2; break; } status = step(I0(), I1()); }
             else status = step(I0(), I0());
             if (status) break;
             d++;

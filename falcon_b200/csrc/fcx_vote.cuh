@@ -423,19 +423,12 @@ k_cns_dp(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, const VoteMeta
             return win[r - wlo];
         };
         __syncwarp();                             // lane 0's record stores are visible to every lane
-        char bb = '$'; int ck = S.g_ck;
+        char bb = '$'; int ck = S.g_ck;           // (a link index >= 5 keeps '$', falcon.c:481)
         unsigned index = 0; const unsigned lim = (unsigned)t_len * 2u;
         int4 r = fetch(S.g_rec);                  // x pred, y info, z score2
         for (;;) {
-            const bool hi = r.y < 0;
-            switch (ck) {
-                case 0: bb = hi ? 'A' : 'a'; break;
-                case 1: bb = hi ? 'C' : 'c'; break;
-                case 2: bb = hi ? 'G' : 'g'; break;
-                case 3: bb = hi ? 'T' : 't'; break;
-                case 4: bb = '-'; break;
-                default: break;
-            }
+            // "ACGT-"[ck], lower case below the coverage threshold (falcon.c:497-512)
+            if ((unsigned)ck < 5u) bb = (char)(((0x2d54474341ull >> (8 * ck)) & 0xffu) | ((r.y >= 0 && ck < 4) ? 0x20u : 0u));
             if (r.x == -1 || index >= lim) break;
             const int4 pr = fetch(r.x);
             if (bb != '-') {
