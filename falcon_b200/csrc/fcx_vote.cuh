@@ -62,20 +62,37 @@ k_vote(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, uint32_t n_tiles
     const int Si = in_seed ? base_at(seed, i) : 0;
     const int Sp = (in_seed && i > 0) ? base_at(seed, i - 1) : 0;
 
-    uint32_t key[VCAP]; uint32_t cnt[VCAP];         // private link table, first-appearance order
+    // private link table, first-appearance order.  The first VREG entries live in registers (the
+    // links that appear first are the frequent ones: a vote is then a few compares, no local-memory
+    // search), the rest in local memory.
+    constexpr int VREG = 4;
+    uint32_t key[VCAP]; uint32_t cnt[VCAP];
+    uint32_t rk0 = 0xffffffffu, rk1 = 0xffffffffu, rk2 = 0xffffffffu, rk3 = 0xffffffffu;     // (no link key has all bits set)
+    uint32_t rc0 = 0, rc1 = 0, rc2 = 0, rc3 = 0;
     int n = 0, coverage = 0, maxd = 0; bool overflow = false;
-    // the dominant link "match after a plain match" is counted in a register; its table slot is
-    // reserved when it first appears so that the order stays the reference's
+    auto append = [&](const uint32_t k, const uint32_t c) {
+        if (n >= VCAP) { overflow = true; return; }
+        if (n == 0) { rk0 = k; rc0 = c; } else if (n == 1) { rk1 = k; rc1 = c; }
+        else if (n == 2) { rk2 = k; rc2 = c; } else if (n == 3) { rk3 = k; rc3 = c; }
+        else { key[n] = k; cnt[n] = c; }
+        n++;
+    };
+    // the dominant link "match after a plain match" is counted in a register of its own; its table slot
+    // is reserved when it first appears so that the order stays the reference's
     const uint32_t k_dom = lk_key(0, Si, (uint32_t)Sp);
     int idx_dom = -1; uint32_t c_dom = 0;
     auto vote = [&](const uint32_t k) {
         if (k == k_dom) {
-            if (idx_dom < 0) { if (n < VCAP) { idx_dom = n; key[n] = k; cnt[n] = 0; n++; } else overflow = true; }
+            if (idx_dom < 0) { idx_dom = n; append(k, 0u); if (overflow) idx_dom = -1; }
             c_dom++;
             return;
         }
-        for (int e = 0; e < n; e++) if (key[e] == k) { cnt[e]++; return; }
-        if (n < VCAP) { key[n] = k; cnt[n] = 1; n++; } else overflow = true;
+        if (k == rk0) { rc0++; return; }
+        if (k == rk1) { rc1++; return; }
+        if (k == rk2) { rc2++; return; }
+        if (k == rk3) { rc3++; return; }
+        for (int e = VREG; e < n; e++) if (key[e] == k) { cnt[e]++; return; }
+        append(k, 1u);
     };
 
     // The block's reads are taken VOTE_TP at a time: the CTA first lists, in read order, those that are
@@ -158,6 +175,7 @@ k_vote(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, uint32_t n_tiles
       }
     }
     if (!in_seed) return;
+    key[0] = rk0; cnt[0] = rc0; key[1] = rk1; cnt[1] = rc1; key[2] = rk2; cnt[2] = rc2; key[3] = rk3; cnt[3] = rc3;
     if (idx_dom >= 0) cnt[idx_dom] = c_dom;
     if (overflow) { atomicMax(err_flag, 1); n = 0; coverage = 0; }
     // ---- write the slot: links stably sorted by delta (the DP needs a level complete before the next)
