@@ -62,37 +62,30 @@ k_vote(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, uint32_t n_tiles
     const int Si = in_seed ? base_at(seed, i) : 0;
     const int Sp = (in_seed && i > 0) ? base_at(seed, i - 1) : 0;
 
-    // private link table, first-appearance order.  The first VREG entries live in registers (the
-    // links that appear first are the frequent ones: a vote is then a few compares, no local-memory
-    // search), the rest in local memory.
-    constexpr int VREG = 4;
-    uint32_t key[VCAP]; uint32_t cnt[VCAP];
-    uint32_t rk0 = 0xffffffffu, rk1 = 0xffffffffu, rk2 = 0xffffffffu, rk3 = 0xffffffffu;     // (no link key has all bits set)
-    uint32_t rc0 = 0, rc1 = 0, rc2 = 0, rc3 = 0;
+    // Link counters of this position.  Every entry carries the index of the read that cast it first
+    // (`ord`), because ties between the links of a column are broken by first appearance (falcon.c:232-263,
+    // :441); the entries are written out sorted by (delta, ord).
+    //   * direct counters for the links that make up almost all votes -- no search:
+    //       delta 0: base {seed base, '-'} x predecessor {read start, (0, seed base of i-1), (0, '-')}   6
+    //       delta 1: inserted base {A,C,G,T} x predecessor (0, {seed base, '-'})                          8
+    //     kept in shared memory, one column of VDIR words per thread: (ord << 16) | count;
+    //     the dominant "match after a plain match" counts in a register;
+    //   * everything else (a delta-0 link after an insertion, deltas >= 2) in a small private table with
+    //     a linear search.
+    constexpr int VDIR = 14;
+    __shared__ uint32_t s_dir[VDIR * VOTE_TP];
+#pragma unroll
+    for (int d = 0; d < VDIR; d++) s_dir[d * VOTE_TP + threadIdx.x] = 0u;
+    uint32_t key[VCAP]; uint32_t cnt[VCAP];         // generic table: key, (ord << 16) | count
     int n = 0, coverage = 0, maxd = 0; bool overflow = false;
-    auto append = [&](const uint32_t k, const uint32_t c) {
-        if (n >= VCAP) { overflow = true; return; }
-        if (n == 0) { rk0 = k; rc0 = c; } else if (n == 1) { rk1 = k; rc1 = c; }
-        else if (n == 2) { rk2 = k; rc2 = c; } else if (n == 3) { rk3 = k; rc3 = c; }
-        else { key[n] = k; cnt[n] = c; }
-        n++;
+    uint32_t c_dom = 0, o_dom = 0;                  // direct entry 1: (0, seed base) after (0, previous seed base)
+    auto vote_direct = [&](const int idx, const uint32_t ord) {
+        const uint32_t v = s_dir[idx * VOTE_TP + threadIdx.x];
+        s_dir[idx * VOTE_TP + threadIdx.x] = v ? v + 1u : ((ord << 16) | 1u);
     };
-    // the dominant link "match after a plain match" is counted in a register of its own; its table slot
-    // is reserved when it first appears so that the order stays the reference's
-    const uint32_t k_dom = lk_key(0, Si, (uint32_t)Sp);
-    int idx_dom = -1; uint32_t c_dom = 0;
-    auto vote = [&](const uint32_t k) {
-        if (k == k_dom) {
-            if (idx_dom < 0) { idx_dom = n; append(k, 0u); if (overflow) idx_dom = -1; }
-            c_dom++;
-            return;
-        }
-        if (k == rk0) { rc0++; return; }
-        if (k == rk1) { rc1++; return; }
-        if (k == rk2) { rc2++; return; }
-        if (k == rk3) { rc3++; return; }
-        for (int e = VREG; e < n; e++) if (key[e] == k) { cnt[e]++; return; }
-        append(k, 1u);
+    auto vote_generic = [&](const uint32_t k, const uint32_t ord) {
+        for (int e = 0; e < n; e++) if (key[e] == k) { cnt[e]++; return; }
+        if (n < VCAP) { key[n] = k; cnt[n] = (ord << 16) | 1u; n++; } else overflow = true;
     };
 
     // The block's reads are taken VOTE_TP at a time: the CTA first lists, in read order, those that are
@@ -134,51 +127,69 @@ k_vote(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, uint32_t n_tiles
         if (lane == 0) ep = (act && i > t_start) ? __ldg(ent_i + i - 1) : 0u;
         if (!act) continue;
         coverage++;
+        const uint32_t ord = s_pair[li];              // read order = first-appearance order
         const int y = i - t_start;
         const int m = (ec & ENT_MATCH) ? 1 : 0, nins = ent_nins(ec);
         const int b0 = m ? Si : 4;
         // query index at this column: only needed to fetch inserted bases beyond the 11 inline ones
         int x = -1;
-        uint32_t pred = LK_START;
-        if (y > 0) {
-            const int pn = ent_nins(ep);
+        const int pn = y > 0 ? ent_nins(ep) : 0;
+        if (pn == 0) {
+            // predecessor: the read starts here, or the previous column without insertion
+            const int pc = y == 0 ? 0 : ((ep & ENT_MATCH) ? 1 : 2);
+            if (m && pc == 1) { if (c_dom == 0) o_dom = ord; c_dom++; }
+            else vote_direct((m ? 0 : 3) + pc, ord);
+        } else {
             int pb;
-            if (pn == 0) pb = (ep & ENT_MATCH) ? Sp : 4;
-            else if (pn <= ENT_INS_INLINE) pb = ent_ins(ep, pn - 1);
+            if (pn <= ENT_INS_INLINE) pb = ent_ins(ep, pn - 1);
             else {
                 const VoteMeta vm = vmeta[bd.pair_begin + s_pair[li]];
                 x = xck_lookup(xck_arena + vm.xck_off, ent_i + t_start, y); pb = base_at(pool + vm.q_woff, vm.q_s + x - 1);
             }
-            pred = ((uint32_t)pn << 3) | (uint32_t)pb;
+            vote_generic(lk_key(0, b0, ((uint32_t)pn << 3) | (uint32_t)pb), ord);
         }
-        vote(lk_key(0, b0, pred));
         if (nins > 0) {
             maxd = max(maxd, nins);
-            int pb = b0;
-            if (nins <= ENT_INS_INLINE) {
-                for (int lev = 1; lev <= nins; lev++) {
-                    const int bb = ent_ins(ec, lev - 1);
-                    vote(lk_key(lev, bb, ((uint32_t)(lev - 1) << 3) | (uint32_t)pb));
-                    pb = bb;
-                }
-            } else {
-                const VoteMeta vm = vmeta[bd.pair_begin + s_pair[li]];
-                if (x < 0) x = xck_lookup(xck_arena + vm.xck_off, ent_i + t_start, y);
-                const uint32_t* qr = pool + vm.q_woff;
-                for (int lev = 1; lev <= nins; lev++) {
-                    const int bb = lev <= ENT_INS_INLINE ? ent_ins(ec, lev - 1) : base_at(qr, vm.q_s + x + m + lev - 1);
-                    vote(lk_key(lev, bb, ((uint32_t)(lev - 1) << 3) | (uint32_t)pb));
-                    pb = bb;
+            int pb = ent_ins(ec, 0);
+            vote_direct(6 + 2 * pb + (m ? 0 : 1), ord);                       // delta 1
+            if (nins > 1) {
+                if (nins <= ENT_INS_INLINE) {
+                    for (int lev = 2; lev <= nins; lev++) {
+                        const int bb = ent_ins(ec, lev - 1);
+                        vote_generic(lk_key(lev, bb, ((uint32_t)(lev - 1) << 3) | (uint32_t)pb), ord);
+                        pb = bb;
+                    }
+                } else {
+                    const VoteMeta vm = vmeta[bd.pair_begin + s_pair[li]];
+                    if (x < 0) x = xck_lookup(xck_arena + vm.xck_off, ent_i + t_start, y);
+                    const uint32_t* qr = pool + vm.q_woff;
+                    for (int lev = 2; lev <= nins; lev++) {
+                        const int bb = lev <= ENT_INS_INLINE ? ent_ins(ec, lev - 1) : base_at(qr, vm.q_s + x + m + lev - 1);
+                        vote_generic(lk_key(lev, bb, ((uint32_t)(lev - 1) << 3) | (uint32_t)pb), ord);
+                        pb = bb;
+                    }
                 }
             }
         }
       }
     }
     if (!in_seed) return;
-    key[0] = rk0; cnt[0] = rc0; key[1] = rk1; cnt[1] = rc1; key[2] = rk2; cnt[2] = rc2; key[3] = rk3; cnt[3] = rc3;
-    if (idx_dom >= 0) cnt[idx_dom] = c_dom;
+    // ---- gather the direct counters into the table
+    if (c_dom) s_dir[1 * VOTE_TP + threadIdx.x] = (o_dom << 16) | c_dom;
+#pragma unroll
+    for (int d = 0; d < VDIR; d++) {
+        const uint32_t v = s_dir[d * VOTE_TP + threadIdx.x];
+        if (v == 0u) continue;
+        uint32_t k;
+        if (d < 6) {
+            const int pc = d % 3;
+            k = lk_key(0, d < 3 ? Si : 4, pc == 0 ? LK_START : (uint32_t)(pc == 1 ? Sp : 4));
+        } else k = lk_key(1, (d - 6) >> 1, (uint32_t)(((d - 6) & 1) ? 4 : Si));
+        if (n < VCAP) { key[n] = k; cnt[n] = v; n++; } else overflow = true;
+    }
     if (overflow) { atomicMax(err_flag, 1); n = 0; coverage = 0; }
-    // ---- write the slot: links stably sorted by delta (the DP needs a level complete before the next)
+    // ---- write the slot: links sorted by delta (the DP needs a level complete before the next), inside a
+    // delta by first appearance
     uint2* slot = slot_arena + (bd.slot_off + (uint64_t)i) * VSLOT;
     uint2* ovf = nullptr; uint32_t ovf_off = 0;
     if (n > VSLOT - 1) {
@@ -187,14 +198,16 @@ k_vote(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, uint32_t n_tiles
         else ovf = ovf_arena + ovf_off;
     }
     slot[0] = make_uint2(((uint32_t)n << 16) | (uint32_t)coverage, ovf_off);
-    int w = 0;
-    for (int lev = 0; lev <= maxd && w < n; lev++)
-        for (int e = 0; e < n; e++)
-            if ((int)(key[e] >> 16) == lev) {
-                const uint2 v = make_uint2(key[e], cnt[e]);
-                if (w < VSLOT - 1) slot[1 + w] = v; else ovf[w - (VSLOT - 1)] = v;
-                w++;
-            }
+    for (int w = 0; w < n; w++) {                  // selection by (delta, ord): n is ~10
+        int best = -1; uint32_t bk = 0xffffffffu;
+        for (int e = 0; e < n; e++) {
+            const uint32_t sk = (key[e] & 0xffff0000u) | (cnt[e] >> 16);      // delta << 16 | ord
+            if (key[e] != 0xffffffffu && sk < bk) { bk = sk; best = e; }      // (two entries of one delta never share ord)
+        }
+        const uint2 v = make_uint2(key[best], cnt[best] & 0xffffu);
+        if (w < VSLOT - 1) slot[1 + w] = v; else ovf[w - (VSLOT - 1)] = v;
+        key[best] = 0xffffffffu;                   // emitted
+    }
 }
 
 // ------------------------------------------------------------------------------ k_cns_dp
