@@ -435,6 +435,7 @@ k_range(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, const PairDesc*
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     uint32_t* sbits = reinterpret_cast<uint32_t*>(s_dyn_all);                 // KTAB / 32 words
     int* hist = s_dyn_all + KTAB / 32 + wib * bins;      // bins >= (max read len + max seed len) / 48 + 2 for this wave
+    __shared__ uint32_t s_next_pair;
     const int n_warps = (int)(blockDim.x >> 5);
     const uint32_t gw = blockIdx.x * n_warps + wib;
     uint32_t* list = list_scratch + (size_t)gw * list_cap;
@@ -443,10 +444,18 @@ k_range(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, const PairDesc*
     const BlockDesc bd = blocks[blk];
     __syncthreads();                                     // every warp is done with the previous bitmap
     for (int j = threadIdx.x; j < KTAB / 32; j += (int)blockDim.x) sbits[j] = __ldg(kbits + (size_t)blk * (KTAB / 32) + j);
+    if (threadIdx.x == 0) s_next_pair = 0u;
     __syncthreads();
     const uint32_t* tab = ktab + (size_t)blk * KTAB;
     const uint32_t* kpos = kpos_arena + bd.kpos_off;
-    for (uint32_t p = bd.pair_begin + wib; p < bd.pair_begin + bd.n_pairs; p += n_warps) {
+    // the block's pairs are handed out dynamically (they differ in read length: a static split leaves
+    // warps waiting at the barrier of the next block)
+    for (;;) {
+        uint32_t pi = 0;
+        if (lane == 0) pi = atomicAdd(&s_next_pair, 1u);
+        pi = __shfl_sync(FULL, pi, 0);
+        if (pi >= bd.n_pairs) break;
+        const uint32_t p = bd.pair_begin + pi;
         const PairDesc pd = pairs[p];
         const uint32_t* read = pool + pd.read_woff;
         const int nq = pd.rlen > KMER ? (pd.rlen - KMER + 3) / 4 : 0;   // i = 0,4,.. < rlen-K
