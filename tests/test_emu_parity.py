@@ -214,3 +214,16 @@ def test_deep_noisy_pileup_takes_the_chunked_consensus_path(emu, oracle):
     emu.upload_pool(seqs)
     got = emu.consensus_blocks([list(range(len(seqs)))], 4, 0.60)[0]
     assert got == oracle.generate_consensus(seqs, 4, 0.60)
+
+
+def test_randomised_parameter_sweep(emu, oracle):
+    """A few random workloads (read length, coverage, error mix, min_cov, min_idt): tools/emu_stress.py runs
+    the long version of this."""
+    rng = np.random.default_rng(2026)
+    for _ in range(6):
+        rl = int(rng.choice([1200, 2500, 4000]))
+        S = synth.make_set(genome_size=int(rl * rng.integers(6, 12)), read_len=rl, coverage=float(rng.choice([8, 15, 25])),
+                           seed=int(rng.integers(1, 1 << 30)), n_blocks=2, p_ins=float(rng.choice([0.02, 0.09, 0.13])),
+                           p_del=float(rng.choice([0.01, 0.045, 0.09])), p_sub=float(rng.choice([0.0, 0.015, 0.04])),
+                           len_sigma=float(rng.choice([0.0, 0.35])), max_n_read=int(rng.choice([12, 200])))
+        G._check_set(emu, oracle, S, int(rng.choice([0, 1, 4])), float(rng.choice([0.6, 0.7, 0.8])))
