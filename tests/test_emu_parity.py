@@ -227,3 +227,21 @@ def test_randomised_parameter_sweep(emu, oracle):
                            p_del=float(rng.choice([0.01, 0.045, 0.09])), p_sub=float(rng.choice([0.0, 0.015, 0.04])),
                            len_sigma=float(rng.choice([0.0, 0.35])), max_n_read=int(rng.choice([12, 200])))
         G._check_set(emu, oracle, S, int(rng.choice([0, 1, 4])), float(rng.choice([0.6, 0.7, 0.8])))
+
+
+def test_query_read_of_exactly_100000_bases(emu, oracle):
+    """consensus.py:178-179 cuts reads only when they are LONGER than 100000; a 100000-base query read is
+    legal (falcon.c:343 limits the seed only).  The engine accepts it; a 100000-base SEED is refused."""
+    from falcon_b200.binding import EngineError
+    rng = np.random.default_rng(9)
+    g = synth.random_codes(100000, rng)
+    seed = synth.codes_to_bytes(g[40000:42500])
+    long_read = synth.codes_to_bytes(g)                              # contains the seed region exactly
+    reads = [synth.codes_to_bytes(synth.add_errors(g[40000:42500], rng, 0.05, 0.03, 0.01)) for _ in range(5)]
+    seqs = [seed, seed, long_read] + reads
+    assert len(long_read) == 100000
+    emu.upload_pool(seqs)
+    got = emu.consensus_blocks([list(range(len(seqs)))], 2, 0.70)[0]
+    assert got == oracle.generate_consensus(seqs, 2, 0.70)
+    with pytest.raises(EngineError):
+        emu.consensus_blocks([[2, 2, 0]], 2, 0.70)
