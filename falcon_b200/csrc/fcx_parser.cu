@@ -31,6 +31,23 @@ struct Block {
 
 inline bool is_space(unsigned char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\v' || c == '\f'; }
 
+// First ASCII-whitespace byte in p[i, n) (or n): eight bytes at a time.  Every whitespace byte is < 0x21, and
+// (x - 0x21..21) & ~x & 0x80..80 flags the LOWEST byte of a word that is < 0x21 exactly (higher flags may be
+// borrow artefacts), so the candidate is checked with is_space and the scan resumes behind it otherwise.
+inline size_t find_space(const char* p, size_t i, size_t n) {
+    while (i + 8 <= n) {
+        uint64_t x;
+        memcpy(&x, p + i, 8);
+        const uint64_t m = (x - 0x2121212121212121ull) & ~x & 0x8080808080808080ull;
+        if (m == 0) { i += 8; continue; }
+        const size_t at = i + (size_t)(__builtin_ctzll(m) >> 3);
+        if (is_space((unsigned char)p[at])) return at;
+        i = at + 1;
+    }
+    while (i < n && !is_space((unsigned char)p[i])) i++;
+    return i;
+}
+
 }  // namespace
 
 struct fcx_parser {
@@ -93,7 +110,7 @@ struct fcx_parser {
             while (i < n && is_space((unsigned char)p[i])) i++;
             if (i >= n) break;
             size_t s = i;
-            while (i < n && !is_space((unsigned char)p[i])) i++;
+            i = find_space(p, i, n);
             if (nt < 2) { tok[nt] = p + s; len[nt] = i - s; }
             nt++;
             if (nt > 2) return;
