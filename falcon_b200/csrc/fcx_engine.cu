@@ -59,7 +59,7 @@ struct Lane {                 // one in-flight wave: stream, events, buffers, st
     cudaStream_t stream = nullptr;
     cudaStream_t stream_hi = nullptr;   // high priority: the latency-bound consensus kernel
     cudaEvent_t ev[8] = {nullptr};
-    DevBuf d_blocks, d_pairs, d_ranges, d_allocs, d_aln, d_ktab, d_kpos, d_trace, d_path, d_xam, d_ent, d_slots,
+    DevBuf d_blocks, d_pairs, d_ranges, d_allocs, d_aln, d_ktab, d_kpos, d_trace, d_path, d_xck, d_ent, d_slots,
            d_ovf, d_vmeta, d_rlist, d_recs, d_lvl, d_cns, d_eqv, d_cnsout, d_counter, d_tbhist, d_order, d_kbits;
     HostBuf h_ranges, h_aln, h_cns, h_cnsout, h_eqv;
     std::string err;
@@ -70,7 +70,7 @@ struct Lane {                 // one in-flight wave: stream, events, buffers, st
     uint32_t rec_scale = 1;            // size factor of the consensus record arena (doubled on retry)
     void release() {
         DevBuf* bufs[] = {&d_blocks, &d_pairs, &d_ranges, &d_allocs, &d_aln, &d_ktab, &d_kpos, &d_trace, &d_path,
-                          &d_xam, &d_ent, &d_slots, &d_ovf, &d_vmeta, &d_rlist, &d_recs, &d_lvl, &d_cns, &d_eqv, &d_cnsout,
+                          &d_xck, &d_ent, &d_slots, &d_ovf, &d_vmeta, &d_rlist, &d_recs, &d_lvl, &d_cns, &d_eqv, &d_cnsout,
                           &d_counter, &d_tbhist, &d_order, &d_kbits};
         for (auto* b : bufs) b->release();
         HostBuf* hb[] = {&h_ranges, &h_aln, &h_cns, &h_cnsout, &h_eqv};
@@ -575,7 +575,7 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
     if (ctx->dp_variant == 3) CKR(L.d_trace.reserve((size_t)std::max(dp_grid, 1u) * DP3_WARPS * max_trace_cap * TRACE_REC_WORDS * 4 + 64));
     else CKR(L.d_trace.reserve(trace_recs * TRACE_REC_WORDS * 4 + 64));
     if (xck_n > 0xffffffffull) { L.err = "out of device memory (checkpoint index)"; return 100; }    // split the wave
-    CKR(L.d_xam.reserve(xck_n * 4 + 128));
+    CKR(L.d_xck.reserve(xck_n * 4 + 128));
     CKR(L.d_ent.reserve(xam_n * 4 + 128));
     CKR(L.d_path.reserve(path_w * 4 + 64));
     if (np) CKL(cudaMemcpyAsync(L.d_allocs.p, ha.data(), (size_t)np * sizeof(PairAlloc), cudaMemcpyHostToDevice, st));
@@ -639,7 +639,7 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
             L.d_blocks.as<BlockDesc>(), L.d_pairs.as<PairDesc>(), L.d_ranges.as<PairRange>(),
             L.d_allocs.as<PairAlloc>(), L.d_order.as<uint32_t>(), L.d_tbhist.as<uint32_t>() + TB_BUCKETS, pool,
             L.d_path.as<uint32_t>(),
-            L.d_xam.as<uint32_t>(), L.d_ent.as<uint32_t>(), L.d_vmeta.as<VoteMeta>(), L.d_aln.as<PairAln>());
+            L.d_xck.as<uint32_t>(), L.d_ent.as<uint32_t>(), L.d_vmeta.as<VoteMeta>(), L.d_aln.as<PairAln>());
         CKL(cudaGetLastError());
         L.counters[FCX_C_KERNEL_LAUNCHES] += 4;
     }
@@ -651,7 +651,7 @@ int run_wave(fcx_ctx* ctx, Lane& L, uint32_t b0, uint32_t b1, const uint32_t* bl
     CKL(cudaMemsetAsync((char*)L.d_counter.p + 16, 0, 16, st));      // [4] overflow cursor, [5] vote error flag
     if (tiles) {
         FCX_LAUNCH(k_vote, (unsigned)tiles, VOTE_TP, 0, st,
-            L.d_blocks.as<BlockDesc>(), nb, (uint32_t)tiles, L.d_vmeta.as<VoteMeta>(), pool, L.d_xam.as<uint32_t>(),
+            L.d_blocks.as<BlockDesc>(), nb, (uint32_t)tiles, L.d_vmeta.as<VoteMeta>(), pool, L.d_xck.as<uint32_t>(),
             L.d_ent.as<uint32_t>(), L.d_slots.as<uint2>(), L.d_ovf.as<uint2>(), ovf_cap_used,
             L.d_counter.as<uint32_t>() + 4, L.d_counter.as<int>() + 5);
         CKL(cudaGetLastError());

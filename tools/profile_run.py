@@ -44,12 +44,6 @@ def main():
         st = eng.stats()
         print("rep %d wall %.1f ms  pairs/s %.0f  " % (r, dt * 1e3, st["pairs"] / dt) +
               " ".join("%s=%.2f" % (k[3:], v) for k, v in st.items() if k.startswith("ms_")), flush=True)
-    prof = (C.c_double * 8)()
-    L.fcx_internal_profile(eng._h, prof)
-    if prof[1] > 0:
-        print("consensus: positions %.0f deep %.0f (%.3f%%)  cycles/pos: vote %.0f dp %.0f generic(per deep) %.0f  backtrack/block %.0f" %
-              (prof[1], prof[0], 100 * prof[0] / prof[1], prof[2] / prof[1], prof[3] / prof[1],
-               prof[4] / max(1.0, prof[0]), prof[5] / len(S.blocks)))
     print("counters:", {k: v for k, v in st.items() if not k.startswith("ms_")})
 
 
