@@ -231,19 +231,6 @@ constexpr int CDP_SL = 12;               // delta levels with shared-memory colu
 constexpr int CDP_LEVELS = 256;          // deltas 0..255 (the tag cut at 255 keeps delta <= 254)
 constexpr int CDP_WIN = 256;             // records per backtrack window
 
-// max over the lanes of `grp` (every lane passes the mask of ITS group; the groups partition the warp and all
-// 32 lanes call together).  One REDUX on the GPU; the SIMT emulator, which keeps a table of the masks it has seen,
-// gets the same result from full-warp shuffles.
-__device__ __forceinline__ int group_max(const unsigned grp, const int v) {
-#ifdef FCX_EMU
-    int m = INT_MIN;
-    for (int l = 0; l < 32; l++) { const int o = __shfl_sync(FULL, v, l); if ((grp >> l) & 1u) m = max(m, o); }
-    return m;
-#else
-    return __reduce_max_sync(grp, v);
-#endif
-}
-
 struct CdpState {                        // per-block running state of the DP
     uint32_t nrec; int g_best2, g_rec, g_ck, err;
 };
@@ -339,7 +326,6 @@ k_cns_dp(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, const VoteMeta
     __shared__ int2 s_tabs[CDP_WARPS][2 * CDP_SL * 5];
     __shared__ int4 s_win[CDP_WARPS][CDP_WIN];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const unsigned lt = lanemask_lt();
     const uint32_t b = blockIdx.x * CDP_WARPS + wib;
     if (b >= n_blocks) return;                    // (no CTA-wide barrier below)
     const BlockDesc bd = blocks[b];
@@ -418,58 +404,28 @@ k_cns_dp(const BlockDesc* __restrict__ blocks, uint32_t n_blocks, const VoteMeta
                 const int2 pv = slotp < CDP_SL * 5 ? s_tab[which * (CDP_SL * 5) + slotp] : gtab[which * (CDP_LEVELS * 5) + slotp];
                 s2 += pv.x; prj = pv.y;
             }
-            unsigned cols = __reduce_or_sync(FULL, mine ? (1u << kk) : 0u);          // live columns of this level
+            unsigned cols = __reduce_or_sync(FULL, mine ? (1u << kk) : 0u);
             const bool reserved0 = i == 0 && L == 0;                                      // column (0,0,'A') owns record 0
             int2* const tab_out = L < CDP_SL ? s_tab + cur * (CDP_SL * 5) + L * 5 : gtab + cur * (CDP_LEVELS * 5) + L * 5;
-            if (!reserved0) {
-                // All live columns of the level at once: lanes of one column form a group (__match_any_sync), the
-                // best link of each column is a max-reduction over its group, the group's lowest lane (the
-                // column's first link) stores the record; records are numbered in base order.
-                const unsigned grp = __match_any_sync(FULL, mine ? (uint32_t)kk : 8u + (uint32_t)lane);
-                const int cb = group_max(grp, mine ? s2 : INT_MIN);
-                const unsigned best_lanes = __ballot_sync(FULL, mine && s2 == cb) & grp;
-                const int wl = mine ? __ffs(best_lanes) - 1 : lane;                       // strict '>' in link order: the FIRST best link wins
-                int col_pred = __shfl_sync(FULL, prj, wl), col_sc2 = cb;
-                if (cb <= -2) { col_sc2 = -2; col_pred = 0; }                             // floored (falcon.c:447)
-                const bool leader = mine && (grp & lt) == 0u;
-                uint32_t ridx = S.nrec + (uint32_t)__popc(cols & ((1u << kk) - 1u));
-                S.nrec += (uint32_t)__popc(cols);
-                if (S.nrec > bd.rec_cap) { S.err = 2; ridx = min(ridx, bd.rec_cap - 1); }
-                if (leader) {
-                    *reinterpret_cast<int4*>(recs + ridx) = make_int4(col_pred, info0 | kk, col_sc2, 0);
-                    tab_out[kk] = make_int2(col_sc2, (int)ridx);
-                }
-                // global best: strict '>' in (delta, base) order (a floored column never wins: g_best2 >= -2)
-                const int lead_sc = leader ? col_sc2 : INT_MIN;
-                const int lvl_best = __reduce_max_sync(FULL, lead_sc);
-                if (lvl_best > S.g_best2) {
-                    const bool top = leader && col_sc2 == lvl_best;
-                    const int bk = __reduce_min_sync(FULL, top ? kk : 99);                // the lowest base among equal columns
-                    const int bl = __ffs(__ballot_sync(FULL, top && kk == bk)) - 1;
-                    S.g_best2 = lvl_best;
-                    S.g_rec = (int)__shfl_sync(FULL, ridx, bl);
-                    S.g_ck = __shfl_sync(FULL, __popc(grp & ((1u << wl) - 1u)), bl);      // index of the best link in its column
-                }
-            } else
-            while (cols) {                                        // (position 0, delta 0 only) live columns one by one, in base order
+            while (cols) {                                        // live columns in base order
                 const int k = __ffs(cols) - 1;
                 cols &= cols - 1u;
                 const bool in_col = mine && kk == k;
                 const int cand = in_col ? s2 : INT_MIN;
-                const int cb = __reduce_max_sync(FULL, cand);
+                const int cb = __reduce_max_sync(FULL, cand);     // strict '>' in link order: the FIRST best link wins
                 const int wl = __ffs(__ballot_sync(FULL, cand == cb)) - 1;               // (lanes outside the column hold INT_MIN < cb)
                 int col_pred = __shfl_sync(FULL, prj, wl), col_sc2 = cb;
-                if (cb <= -2) { col_sc2 = -2; col_pred = 0; }
+                if (cb <= -2) { col_sc2 = -2; col_pred = 0; }                             // floored (falcon.c:447)
                 uint32_t ridx = S.nrec;
-                if (k == 0) ridx = 0; else S.nrec++;
+                if (reserved0 && k == 0) ridx = 0; else S.nrec++;
                 if (ridx >= bd.rec_cap) { S.err = 2; ridx = bd.rec_cap - 1; }
                 if (lane == 0) {
                     *reinterpret_cast<int4*>(recs + ridx) = make_int4(col_pred, info0 | k, col_sc2, 0);
                     tab_out[k] = make_int2(col_sc2, (int)ridx);
                 }
-                if (col_sc2 > S.g_best2) {
+                if (col_sc2 > S.g_best2) {                        // (a floored column never gets here: g_best2 >= -2)
                     S.g_best2 = col_sc2; S.g_rec = (int)ridx;
-                    S.g_ck = __popc(__ballot_sync(FULL, in_col) & ((1u << wl) - 1u));
+                    S.g_ck = __popc(__ballot_sync(FULL, in_col) & ((1u << wl) - 1u));     // index of the best link in its column
                 }
             }
             __syncwarp();                                         // the next level (or position) reads these columns
