@@ -117,3 +117,34 @@ def test_native_parser_matches_python_restatement():
             got = _native_blocks(txt, *params, chunk)
             assert got == want, (params, chunk)
     assert len(_python_blocks(txt, 1, 0, 500, 0, 0)) >= 5
+
+
+def test_native_parser_parallel_feed_matches_python_model(monkeypatch):
+    """Chunks with three or more control lines are parsed block-parallel (worker threads with fresh state);
+    the result must not depend on the thread count, the chunking, or where a chunk cuts a line."""
+    import random
+    rnd = random.Random(11)
+
+    def seq(n):
+        return "".join(rnd.choice("ACGT") for _ in range(n))
+    lines = []
+    for b in range(40):
+        sid = "s%d" % b
+        lines.append("%s %s" % (sid, seq(rnd.randint(50, 900))))
+        for r in range(rnd.randint(0, 12)):
+            lines.append("%s %s" % (rnd.choice(["r%d_%d" % (b, r), sid, "r%d_0" % b]), seq(rnd.randint(1, 1200))))
+        if rnd.random() < 0.15:
+            lines.append("+ one two")                      # three tokens: not a control line
+        if rnd.random() < 0.15:
+            lines.append("  +\t" + seq(30))                # "+" with a sequence as second token IS a control line
+        else:
+            lines.append(rnd.choice(["+ +", "+ +", "* *", " + + "]))
+    lines += ["tail1 " + seq(400), "tail2 " + seq(300), "+ +", "- -", "after " + seq(100), "+ +"]
+    txt = ("\n".join(lines) + "\n").encode()
+    want = _python_blocks(txt, 2, 0, 8, 0, 0)
+    assert len(want) > 15
+    monkeypatch.setenv("FCX_PARSER_PAR_MIN", "0")
+    for threads in ("1", "2", "5"):
+        monkeypatch.setenv("FCX_PARSER_THREADS", threads)
+        for chunk in (997, 20000, 1 << 22):
+            assert _native_blocks(txt, 2, 0, 8, 0, 0, chunk) == want, (threads, chunk)
